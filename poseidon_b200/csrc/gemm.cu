@@ -1,0 +1,432 @@
+// tcgen05 GEMM for every Linear / 1x1-conv on the scOT hot path (forward, dgrad, wgrad).
+//
+//   D[m, n] = sum_k A(m, k) * B(n, k)      bf16 operands, fp32 accumulation in TMEM
+//
+// Replaces the cuBLAS calls behind nn.Linear in the reference:
+//   Swinv2SelfAttention.query/key/value (HF modeling_swinv2.py:416-418), Swinv2SelfOutput.dense (:531),
+//   Swinv2Intermediate.dense (:571), Swinv2Output.dense (:586), ScOTPatchMerging.reduction
+//   (scOT/model.py:669), ScOTPatchUnmerging.upsample/mixup (:725-726), ConvNeXtBlock.pwconv1/2 (:186-190)
+// and their autograd backward (dgrad: B operand MN-major = the same weight read transposed;
+// wgrad: both operands MN-major with the token dimension as the reduction, split over CTAs).
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
+//   warps 2..5  : epilogue: tcgen05.ld (32x32b) -> registers -> fp32 staging in (re-used) pipeline smem
+//                 -> coalesced 128-bit global stores with the fused op (bias / GELU / GELU' / RMW / red.add)
+// Tails in M, N and K are handled by TMA out-of-bounds zero fill + predicated stores.
+#include "common.cuh"
+#include "scot_b200.h"
+
+namespace {
+
+constexpr int BM = 128;       // UMMA M (cta_group::1)
+constexpr int BK = 64;        // bf16 elements per k-block = one 128B swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+constexpr int EPI_THREADS = 128;
+
+struct EpiArgs {
+  const float* bias;
+  void* out0;
+  long ld0;
+  void* out1;
+  long ld1;
+  const void* aux;
+  long ldaux;
+  float* colsum;
+};
+
+// ---- fused epilogue on a float4 of accumulators at (row, col..col+3); col is a multiple of 4 ----------
+template <int MODE>
+__device__ __forceinline__ void epi_store(const EpiArgs& ep, long row, int col, float4 v, float4& csum) {
+  if (ep.bias != nullptr) {
+    const float4 b = *reinterpret_cast<const float4*>(ep.bias + col);
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  if constexpr (MODE == SCOT_EPI_BF16) {
+    uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + row * ep.ld0 + col) = o;
+  } else if constexpr (MODE == SCOT_EPI_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + row * ep.ld0 + col) = v;
+  } else if constexpr (MODE == SCOT_EPI_GELU) {
+    // out0 = pre-activation h (saved for backward), out1 = gelu_erf(h). h is rounded to bf16 first so
+    // that forward and backward see the same pre-activation.
+    float hx = bf16_round(v.x), hy = bf16_round(v.y), hz = bf16_round(v.z), hw = bf16_round(v.w);
+    uint2 o0 = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
+    uint2 o1 = make_uint2(pack_bf16x2(gelu_erf(hx), gelu_erf(hy)), pack_bf16x2(gelu_erf(hz), gelu_erf(hw)));
+    if (ep.out0 != nullptr)
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + row * ep.ld0 + col) = o0;
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out1) + row * ep.ld1 + col) = o1;
+  } else if constexpr (MODE == SCOT_EPI_GELU_BWD) {
+    const uint2 hraw = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + row * ep.ldaux + col);
+    const float2 h01 = unpack_bf16x2(hraw.x), h23 = unpack_bf16x2(hraw.y);
+    v.x *= gelu_erf_grad(h01.x); v.y *= gelu_erf_grad(h01.y);
+    v.z *= gelu_erf_grad(h23.x); v.w *= gelu_erf_grad(h23.y);
+    uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + row * ep.ld0 + col) = o;
+    const float2 r01 = unpack_bf16x2(o.x), r23 = unpack_bf16x2(o.y);  // column sums of what was stored
+    csum.x += r01.x; csum.y += r01.y; csum.z += r23.x; csum.w += r23.y;
+  } else if constexpr (MODE == SCOT_EPI_RMW_F32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + row * ep.ld0 + col);
+    float4 o = *p;
+    o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+    *p = o;
+  } else if constexpr (MODE == SCOT_EPI_ATOMIC_F32) {
+    float* p = reinterpret_cast<float*>(ep.out0) + row * ep.ld0 + col;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  } else if constexpr (MODE == SCOT_EPI_ADD_F32_BF16) {
+    // out0 (fp32) = acc + aux (fp32 residual); out1 (bf16 copy) = same value rounded
+    const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.aux) + row * ep.ldaux + col);
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + row * ep.ld0 + col) = v;
+    if (ep.out1 != nullptr) {
+      uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out1) + row * ep.ld1 + col) = o;
+    }
+  }
+}
+
+// =================================================================================================
+// tcgen05 kernel
+// =================================================================================================
+template <int BN>
+struct TileCfg {
+  static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kABytes = BM * BK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagePitch = BN + 4;  // floats; +4 keeps 128-bit smem accesses conflict free
+  static constexpr int kStagingBytes = BM * kStagePitch * 4;
+};
+
+template <int BN, int AMN, int BMN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+               int kblocks_total, int kblocks_per_split, int num_stages, EpiArgs ep) {
+  using Cfg = TileCfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [0,1024) barriers + tmem ptr ; then 1024-aligned stages
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = empty_bar + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint8_t* tiles = smem + 1024;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int kb_begin = blockIdx.z * kblocks_per_split;
+  const int kb_end = min(kb_begin + kblocks_per_split, kblocks_total);
+  const int nkb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % num_stages;
+        const uint32_t ph = (uint32_t)(i / num_stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        uint8_t* sa = tiles + (size_t)s * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        const int k0 = (kb_begin + i) * BK;
+        if constexpr (AMN == 0) {
+          tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {64 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], m0 + 64 * j, k0);
+        }
+        if constexpr (BMN == 0) {
+          tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {64 k, BN rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + 64 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, AMN, BMN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % num_stages;
+        const uint32_t ph = (uint32_t)(i / num_stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + (size_t)s * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major: advance 16 elements = 32 B inside the swizzle atom. MN-major: advance 16 k-rows = 2048 B.
+          const uint64_t da = (AMN == 0) ? umma_smem_desc(sa + k * 32, 16, 1024)
+                                         : umma_smem_desc(sa + k * 2048, BK * 128, 1024);
+          const uint64_t db = (BMN == 0) ? umma_smem_desc(sb + k * 32, 16, 1024)
+                                         : umma_smem_desc(sb + k * 2048, BK * 128, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int et = (warp - 2) * 32 + lane;
+    float* stage = reinterpret_cast<float*>(tiles);
+    if (nkb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const int r = q * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(stage + (size_t)r * Cfg::kStagePitch + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      tc_fence_before();
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+    if (nkb > 0) {
+      constexpr int VPR = BN / 4;              // float4 per tile row
+      constexpr int RPP = EPI_THREADS / VPR;   // rows per pass
+      const int cv = et % VPR;
+      const int r0 = et / VPR;
+      const int col = n0 + cv * 4;
+      float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 < RPP && col < N) {
+        for (int r = r0; r < BM; r += RPP) {
+          const long row = (long)m0 + r;
+          if (row >= M) break;
+          const float4 v = *reinterpret_cast<const float4*>(stage + (size_t)r * Cfg::kStagePitch + cv * 4);
+          epi_store<MODE>(ep, row, col, v, csum);
+        }
+        if constexpr (MODE == SCOT_EPI_GELU_BWD) {
+          if (ep.colsum != nullptr) {
+            atomicAdd(ep.colsum + col + 0, csum.x);
+            atomicAdd(ep.colsum + col + 1, csum.y);
+            atomicAdd(ep.colsum + col + 2, csum.z);
+            atomicAdd(ep.colsum + col + 3, csum.w);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// =================================================================================================
+// SIMT reference kernel (bring-up / cross-check path; same epilogue semantics, fp32 FMA on CUDA cores)
+// =================================================================================================
+template <int MODE>
+__global__ void gemm_simt_kernel(const bf16* __restrict__ A, long lda, int amn, const bf16* __restrict__ B, long ldb,
+                                 int bmn, int M, int N, int K, EpiArgs ep) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long row = (long)blockIdx.y * blockDim.y + threadIdx.y;
+  if (row >= M || col >= N) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < K; ++k) {
+    const float a = __bfloat162float(amn ? A[(long)k * lda + row] : A[row * lda + k]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float b = __bfloat162float(bmn ? B[(long)k * ldb + col + j] : B[(long)(col + j) * ldb + k]);
+      acc[j] = fmaf(a, b, acc[j]);
+    }
+  }
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+  epi_store<MODE>(ep, row, col, make_float4(acc[0], acc[1], acc[2], acc[3]), csum);
+  if constexpr (MODE == SCOT_EPI_GELU_BWD) {
+    if (ep.colsum != nullptr) {
+      atomicAdd(ep.colsum + col + 0, csum.x);
+      atomicAdd(ep.colsum + col + 1, csum.y);
+      atomicAdd(ep.colsum + col + 2, csum.z);
+      atomicAdd(ep.colsum + col + 3, csum.w);
+    }
+  }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_encode = nullptr;
+
+int get_encode_fn() {
+  if (g_encode != nullptr) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  SCOT_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  SCOT_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return 0;
+}
+
+// inner = contiguous dimension (elements), outer = strided dimension, ld = stride of outer in elements
+int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+              uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SCOT_REQUIRE(r == CUDA_SUCCESS,
+               "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, ptr,
+               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+  return 0;
+}
+
+int g_num_sms = 0;
+
+template <int BN, int AMN, int BMN, int MODE>
+int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
+              cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (AMN == 0) rc = make_tmap(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+  else rc = make_tmap(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  if (rc) return rc;
+  if (BMN == 0) rc = make_tmap(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
+  else rc = make_tmap(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
+
+  const int tiles_m = ceil_div(M, BM), tiles_n = ceil_div(N, BN);
+  const int kblocks = ceil_div(K, BK);
+  int splits = 1;
+  if (MODE == SCOT_EPI_ATOMIC_F32) {
+    // split the (long) reduction so that the grid covers ~2 waves of the machine
+    const int target = 2 * g_num_sms;
+    splits = target / (tiles_m * tiles_n);
+    if (splits < 1) splits = 1;
+    if (splits > kblocks) splits = kblocks;
+  }
+  int kps = ceil_div(kblocks, splits);
+  splits = ceil_div(kblocks, kps);  // no empty split
+
+  int min_stages = ceil_div(Cfg::kStagingBytes, Cfg::kStageBytes);
+  int stages = kps < 4 ? kps : 4;
+  if (stages < min_stages) stages = min_stages;
+  if (stages < 2) stages = 2;
+  SCOT_REQUIRE(stages <= 8, "gemm: too many stages");
+  const size_t smem = 1024 /*align slack*/ + 1024 /*barriers*/ + (size_t)stages * Cfg::kStageBytes;
+  SCOT_REQUIRE(smem <= 227 * 1024, "gemm: smem %zu too large", smem);
+  auto kern = gemm_tc_kernel<BN, AMN, BMN, MODE>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  dim3 grid(tiles_n, tiles_m, splits);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, M, N, kblocks, kps, stages, ep);
+  SCOT_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int AMN, int BMN, int MODE>
+int dispatch_bn(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
+                cudaStream_t stream) {
+  if (BMN == 0) {
+    if (N % 128 == 0) return launch_tc<128, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+    if (N % 96 == 0) return launch_tc<96, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+    if (N > 64) return launch_tc<128, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+    return launch_tc<64, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+  } else {
+    if (N > 64) return launch_tc<128, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+    return launch_tc<64, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+  }
+}
+
+template <int MODE>
+int launch_simt(const void* A, long lda, int amn, const void* B, long ldb, int bmn, int M, int N, int K,
+                const EpiArgs& ep, cudaStream_t stream) {
+  dim3 block(32, 8);
+  dim3 grid(ceil_div(N, 32 * 4), ceil_div(M, 8));
+  gemm_simt_kernel<MODE><<<grid, block, 0, stream>>>(reinterpret_cast<const bf16*>(A), lda, amn,
+                                                     reinterpret_cast<const bf16*>(B), ldb, bmn, M, N, K, ep);
+  SCOT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+int scot_gemm_launch(const void* A, long lda, int a_mn_major, const void* B, long ldb, int b_mn_major, int M, int N,
+                     int K, const ScotEpilogue* e, int impl, cudaStream_t stream) {
+  SCOT_REQUIRE(A && B && e && e->out0, "gemm: null pointer");
+  SCOT_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %d %d %d", M, N, K);
+  SCOT_REQUIRE(N % 4 == 0, "gemm: N=%d must be a multiple of 4", N);
+  SCOT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: leading dimensions must be multiples of 8 (16 B rows)");
+  SCOT_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "gemm: operands must be 16 B aligned");
+  EpiArgs ep{e->bias, e->out0, e->ld0, e->out1, e->ld1, e->aux, e->ldaux, e->colsum};
+  if (g_num_sms == 0) {
+    int dev = 0;
+    SCOT_CHECK_CUDA(cudaGetDevice(&dev));
+    SCOT_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (impl == SCOT_GEMM_SIMT) {
+    switch (e->mode) {
+#define SIMT_CASE(MD) \
+  case MD: return launch_simt<MD>(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, ep, stream);
+      SIMT_CASE(SCOT_EPI_BF16)
+      SIMT_CASE(SCOT_EPI_F32)
+      SIMT_CASE(SCOT_EPI_GELU)
+      SIMT_CASE(SCOT_EPI_GELU_BWD)
+      SIMT_CASE(SCOT_EPI_RMW_F32)
+      SIMT_CASE(SCOT_EPI_ATOMIC_F32)
+      SIMT_CASE(SCOT_EPI_ADD_F32_BF16)
+#undef SIMT_CASE
+      default: SCOT_REQUIRE(false, "gemm: unknown epilogue mode %d", e->mode);
+    }
+  }
+  int rc = get_encode_fn();
+  if (rc) return rc;
+  const int majors = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+#define TC_CASE(AM, BM_, MD) \
+  if (majors == ((AM ? 2 : 0) | (BM_ ? 1 : 0)) && e->mode == MD) \
+    return dispatch_bn<AM, BM_, MD>(A, lda, B, ldb, M, N, K, ep, stream);
+  // forward (x @ W^T): both K-major
+  TC_CASE(0, 0, SCOT_EPI_BF16)
+  TC_CASE(0, 0, SCOT_EPI_F32)
+  TC_CASE(0, 0, SCOT_EPI_GELU)
+  TC_CASE(0, 0, SCOT_EPI_ADD_F32_BF16)
+  // dgrad (dy @ W): weight read MN-major
+  TC_CASE(0, 1, SCOT_EPI_BF16)
+  TC_CASE(0, 1, SCOT_EPI_F32)
+  TC_CASE(0, 1, SCOT_EPI_GELU_BWD)
+  TC_CASE(0, 1, SCOT_EPI_RMW_F32)
+  // wgrad (dy^T @ x): both MN-major, split reduction, fp32 red.add into the gradient buffer
+  TC_CASE(1, 1, SCOT_EPI_ATOMIC_F32)
+  TC_CASE(1, 1, SCOT_EPI_F32)
+#undef TC_CASE
+  SCOT_REQUIRE(false, "gemm: unsupported combination a_mn=%d b_mn=%d mode=%d", a_mn_major, b_mn_major, e->mode);
+}
