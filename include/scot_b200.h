@@ -69,6 +69,71 @@ typedef struct ScotEpilogue {
 int scot_gemm_bf16(const void* A, long lda, int a_mn_major, const void* B, long ldb, int b_mn_major, int M, int N,
                    int K, const ScotEpilogue* epi, int impl, void* stream);
 
+
+/* ---- per-op entry points (used by the parity tests; the engine below calls the same launchers) ------
+ * Layouts: activations are token-major [batch*res*res, C]; "f32"/"bf16" name the element type. */
+
+/* ConditionalLayerNorm / LayerNorm forward (scOT/model.py:135-160) fused with the residual add and the
+ * bf16 down-cast. y = (aw*t+ab) * zhat + (cw*t+cb) [+ residual]; aw/cw NULL => plain LayerNorm(ab, cb).
+ * perm_res > 0 applies ScOTPatchUnmerging's pixel-shuffle row permutation (model.py:748-754). */
+int scot_cln_fwd(const float* z, const float* residual, const float* time, const float* aw, const float* ab,
+                 const float* cw, const float* cb, float* x_out, void* xb_out, void* zhat, float* rstd, long rows, int C,
+                 int rows_per_sample, int perm_res, float eps, void* stream);
+/* backward: dz (bf16 or f32) and atomically accumulated parameter gradients; g_bias_prev += colsum(dz) */
+int scot_cln_bwd(const float* dy, const void* zhat, const float* rstd, const float* time, const float* aw,
+                 const float* ab, void* dz, int dz_is_f32, float* g_aw, float* g_ab, float* g_cw, float* g_cb,
+                 float* g_bias_prev, long rows, int C, int rows_per_sample, int perm_res, void* stream);
+
+/* continuous relative position bias (HF modeling_swinv2.py:450-460,489-510):
+ * tab2[r,h] = 16*sigmoid(mlp(coords[r]))[h]*log2(e), alpha[h] = exp(min(logit_scale[h], ln 100)) */
+int scot_cpb_fwd(const float* w1, const float* b1, const float* w2, const float* logit_scale, float* tab2, float* alpha,
+                 int ws, int heads, void* stream);
+int scot_cpb_bwd(const float* w1, const float* b1, const float* w2, const float* logit_scale, const float* dtab,
+                 const float* dalpha, float* dpre_ws, float* g_w1, float* g_b1, float* g_w2, float* g_ls, int ws, int heads,
+                 void* stream);
+/* shifted-window cosine attention (HF:421-487 + scOT/model.py:522-559) on qkv [tokens, 3C] bf16 */
+int scot_attn_fwd(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, int batch, int res, int ws,
+                  int shift, int heads, int head_dim, void* stream);
+size_t scot_attn_bwd_partial_bytes(int ws, int heads, int total_windows);
+int scot_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, const float* tab2, const float* alpha,
+                  void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha, float* g_qbias,
+                  float* g_vbias, int batch, int res, int ws, int shift, int heads, int head_dim, void* stream);
+
+/* ---- whole-model engine --------------------------------------------------------------------------
+ * Mirrors ScOTConfig (scOT/model.py:66-132); replaces ScOT.forward (:1318-1509) + autograd backward. */
+typedef struct ScotModelDesc {
+  int image_size, patch_size, num_channels, num_out_channels, embed_dim, num_stages;
+  int depths[4], num_heads[4], skip_blocks[4];
+  int window_size;
+  float mlp_ratio;
+  int use_conditioning, learn_residual, loss_p;
+  int n_slices;   /* 0: plain l1/mse; else len(channel_slice_list_normalized_loss) */
+  int slices[10];
+  float layer_norm_eps;
+} ScotModelDesc;
+
+typedef struct ScotEngine ScotEngine;
+
+int scot_engine_create(const ScotModelDesc* desc, int batch, ScotEngine** out);
+void scot_engine_destroy(ScotEngine* e);
+/* parameter table: names are the reference's state_dict keys; offsets index one flat fp32 buffer of
+ * scot_engine_param_elems() elements that the caller allocates (zero filled) and the parameters view. */
+long scot_engine_num_params(const ScotEngine* e);
+long scot_engine_param_elems(const ScotEngine* e);
+int scot_engine_param_info(const ScotEngine* e, long i, char* name, int name_cap, long* offset, long* numel, int* ndim,
+                           long* shape4);
+size_t scot_engine_workspace_bytes(const ScotEngine* e);
+/* forward: pixel_values [B,Cin,H,W] f32, time [B] f32 or NULL, labels [B,Cout,H,W] f32 or NULL,
+ * mask: uint8 [B,Cout] (mask_mode 1) or [B,Cout,H,W] (mask_mode 2) or NULL (0); pred_out [B,Cout,H,W],
+ * loss_out [1]. The arena (scot_engine_workspace_bytes, 256 B aligned) keeps the activations for backward. */
+int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const float* pixel_values, const float* time,
+                        const float* labels, const uint8_t* mask, int mask_mode, float* pred_out, float* loss_out,
+                        int gemm_impl, void* stream);
+/* backward of the last forward: grads (same layout as params) += d(grad_loss*loss + <grad_pred, pred>)/dparams.
+ * grad_loss: device scalar or NULL; grad_pred: [B,Cout,H,W] or NULL. Gradients are accumulated, never zeroed. */
+int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void* arena, const float* grad_loss,
+                         const float* grad_pred, int gemm_impl, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,3 +84,133 @@ def gemm(A, B, M, N, K, *, a_mn=False, b_mn=False, mode=EPI_BF16, bias=None, out
     rc = lib.scot_gemm_bf16(ptr(A), A.stride(0), int(a_mn), ptr(B), B.stride(0), int(b_mn), M, N, K, C.byref(e),
                             impl, cur_stream())
     check(rc, "scot_gemm_bf16")
+
+
+# ---------------------------------------------------------------------------------------------------
+# per-op wrappers (tests) and the whole-model engine
+# ---------------------------------------------------------------------------------------------------
+class ScotModelDesc(C.Structure):
+    _fields_ = [
+        ("image_size", C.c_int), ("patch_size", C.c_int), ("num_channels", C.c_int), ("num_out_channels", C.c_int),
+        ("embed_dim", C.c_int), ("num_stages", C.c_int),
+        ("depths", C.c_int * 4), ("num_heads", C.c_int * 4), ("skip_blocks", C.c_int * 4),
+        ("window_size", C.c_int), ("mlp_ratio", C.c_float),
+        ("use_conditioning", C.c_int), ("learn_residual", C.c_int), ("loss_p", C.c_int),
+        ("n_slices", C.c_int), ("slices", C.c_int * 10), ("layer_norm_eps", C.c_float),
+    ]
+
+
+def _declare_engine(lib):
+    vp, i, l, f = C.c_void_p, C.c_int, C.c_long, C.c_float
+    lib.scot_cln_fwd.argtypes = [vp] * 11 + [l, i, i, i, f, vp]
+    lib.scot_cln_fwd.restype = i
+    lib.scot_cln_bwd.argtypes = [vp] * 7 + [i] + [vp] * 5 + [l, i, i, i, vp]
+    lib.scot_cln_bwd.restype = i
+    lib.scot_cpb_fwd.argtypes = [vp] * 6 + [i, i, vp]
+    lib.scot_cpb_fwd.restype = i
+    lib.scot_cpb_bwd.argtypes = [vp] * 11 + [i, i, vp]
+    lib.scot_cpb_bwd.restype = i
+    lib.scot_attn_fwd.argtypes = [vp] * 5 + [i] * 6 + [vp]
+    lib.scot_attn_fwd.restype = i
+    lib.scot_attn_bwd_partial_bytes.argtypes = [i, i, i]
+    lib.scot_attn_bwd_partial_bytes.restype = C.c_size_t
+    lib.scot_attn_bwd.argtypes = [vp] * 8 + [C.c_size_t] + [vp] * 4 + [i] * 6 + [vp]
+    lib.scot_attn_bwd.restype = i
+    lib.scot_engine_create.argtypes = [C.POINTER(ScotModelDesc), i, C.POINTER(vp)]
+    lib.scot_engine_create.restype = i
+    lib.scot_engine_destroy.argtypes = [vp]
+    lib.scot_engine_destroy.restype = None
+    lib.scot_engine_num_params.argtypes = [vp]
+    lib.scot_engine_num_params.restype = l
+    lib.scot_engine_param_elems.argtypes = [vp]
+    lib.scot_engine_param_elems.restype = l
+    lib.scot_engine_param_info.argtypes = [vp, l, C.c_char_p, i, C.POINTER(l), C.POINTER(l), C.POINTER(i), C.POINTER(l)]
+    lib.scot_engine_param_info.restype = i
+    lib.scot_engine_workspace_bytes.argtypes = [vp]
+    lib.scot_engine_workspace_bytes.restype = C.c_size_t
+    lib.scot_engine_forward.argtypes = [vp] * 7 + [i, vp, vp, i, vp]
+    lib.scot_engine_forward.restype = i
+    lib.scot_engine_backward.argtypes = [vp] * 6 + [i, vp]
+    lib.scot_engine_backward.restype = i
+
+
+_declare_base = _declare
+
+
+def _declare(lib):  # noqa: F811  (extends the GEMM-only declaration above)
+    _declare_base(lib)
+    _declare_engine(lib)
+
+
+def cln_fwd(z, residual, time, aw, ab, cw, cb, x_out, xb_out, zhat, rstd, rows, Cdim, rows_per_sample, perm_res=0,
+            eps=1e-5):
+    check(load().scot_cln_fwd(ptr(z), ptr(residual), ptr(time), ptr(aw), ptr(ab), ptr(cw), ptr(cb), ptr(x_out),
+                              ptr(xb_out), ptr(zhat), ptr(rstd), rows, Cdim, rows_per_sample, perm_res, eps, cur_stream()),
+          "scot_cln_fwd")
+
+
+def cln_bwd(dy, zhat, rstd, time, aw, ab, dz, dz_is_f32, g_aw, g_ab, g_cw, g_cb, g_bias_prev, rows, Cdim,
+            rows_per_sample, perm_res=0):
+    check(load().scot_cln_bwd(ptr(dy), ptr(zhat), ptr(rstd), ptr(time), ptr(aw), ptr(ab), ptr(dz), int(dz_is_f32),
+                              ptr(g_aw), ptr(g_ab), ptr(g_cw), ptr(g_cb), ptr(g_bias_prev), rows, Cdim, rows_per_sample,
+                              perm_res, cur_stream()), "scot_cln_bwd")
+
+
+def cpb_fwd(w1, b1, w2, ls, tab2, alpha, ws, heads):
+    check(load().scot_cpb_fwd(ptr(w1), ptr(b1), ptr(w2), ptr(ls), ptr(tab2), ptr(alpha), ws, heads, cur_stream()),
+          "scot_cpb_fwd")
+
+
+def cpb_bwd(w1, b1, w2, ls, dtab, dalpha, dpre, g_w1, g_b1, g_w2, g_ls, ws, heads):
+    check(load().scot_cpb_bwd(ptr(w1), ptr(b1), ptr(w2), ptr(ls), ptr(dtab), ptr(dalpha), ptr(dpre), ptr(g_w1), ptr(g_b1),
+                              ptr(g_w2), ptr(g_ls), ws, heads, cur_stream()), "scot_cpb_bwd")
+
+
+def attn_fwd(qkv, out, lse, tab2, alpha, batch, res, ws, shift, heads, hd):
+    check(load().scot_attn_fwd(ptr(qkv), ptr(out), ptr(lse), ptr(tab2), ptr(alpha), batch, res, ws, shift, heads, hd,
+                               cur_stream()), "scot_attn_fwd")
+
+
+def attn_bwd(qkv, o, d_o, lse, tab2, alpha, dqkv, partial, dtab, dalpha, g_qbias, g_vbias, batch, res, ws, shift, heads,
+             hd):
+    check(load().scot_attn_bwd(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(tab2), ptr(alpha), ptr(dqkv), ptr(partial),
+                               partial.numel() * partial.element_size(), ptr(dtab), ptr(dalpha), ptr(g_qbias),
+                               ptr(g_vbias), batch, res, ws, shift, heads, hd, cur_stream()), "scot_attn_bwd")
+
+
+class Engine:
+    """Host handle of the native engine for one (config, batch) pair. Owns no device memory."""
+
+    def __init__(self, desc: ScotModelDesc, batch: int):
+        lib = load()
+        self._lib = lib
+        h = C.c_void_p()
+        check(lib.scot_engine_create(C.byref(desc), batch, C.byref(h)), "scot_engine_create")
+        self.handle = h
+        self.batch = batch
+        self.param_elems = lib.scot_engine_param_elems(h)
+        self.workspace_bytes = lib.scot_engine_workspace_bytes(h)
+        self.table = {}
+        buf = C.create_string_buffer(512)
+        off, num, nd = C.c_long(), C.c_long(), C.c_int()
+        shp = (C.c_long * 4)()
+        for i in range(lib.scot_engine_num_params(h)):
+            check(lib.scot_engine_param_info(h, i, buf, 512, C.byref(off), C.byref(num), C.byref(nd), shp))
+            self.table[buf.value.decode()] = (off.value, num.value, tuple(shp[k] for k in range(nd.value)))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._lib.scot_engine_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def forward(self, params, arena, pixel_values, time, labels, mask, mask_mode, pred, loss, impl=GEMM_TCGEN05):
+        check(self._lib.scot_engine_forward(self.handle, ptr(params), ptr(arena), ptr(pixel_values), ptr(time),
+                                            ptr(labels), ptr(mask), mask_mode, ptr(pred), ptr(loss), impl, cur_stream()),
+              "scot_engine_forward")
+
+    def backward(self, params, grads, arena, grad_loss, grad_pred, impl=GEMM_TCGEN05):
+        check(self._lib.scot_engine_backward(self.handle, ptr(params), ptr(grads), ptr(arena), ptr(grad_loss),
+                                             ptr(grad_pred), impl, cur_stream()), "scot_engine_backward")

@@ -29,4 +29,37 @@ int scot_gemm_bf16(const void* A, long lda, int a_mn_major, const void* B, long 
   return scot_gemm_launch(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epi, impl, (cudaStream_t)stream);
 }
 
+int scot_cln_fwd(const float* z, const float* residual, const float* time, const float* aw, const float* ab,
+                 const float* cw, const float* cb, float* x_out, void* xb_out, void* zhat, float* rstd, long rows, int C,
+                 int rows_per_sample, int perm_res, float eps, void* stream) {
+  return scot_cln_fwd_launch(z, residual, time, aw, ab, cw, cb, x_out, xb_out, zhat, rstd, rows, C, rows_per_sample,
+                             perm_res, eps, (cudaStream_t)stream);
+}
+int scot_cln_bwd(const float* dy, const void* zhat, const float* rstd, const float* time, const float* aw,
+                 const float* ab, void* dz, int dz_is_f32, float* g_aw, float* g_ab, float* g_cw, float* g_cb,
+                 float* g_bias_prev, long rows, int C, int rows_per_sample, int perm_res, void* stream) {
+  return scot_cln_bwd_launch(dy, zhat, rstd, time, aw, ab, dz, dz_is_f32, g_aw, g_ab, g_cw, g_cb, g_bias_prev, rows, C,
+                             rows_per_sample, perm_res, (cudaStream_t)stream);
+}
+int scot_cpb_fwd(const float* w1, const float* b1, const float* w2, const float* logit_scale, float* tab2, float* alpha,
+                 int ws, int heads, void* stream) {
+  return scot_cpb_fwd_launch(w1, b1, w2, logit_scale, tab2, alpha, ws, heads, (cudaStream_t)stream);
+}
+int scot_cpb_bwd(const float* w1, const float* b1, const float* w2, const float* logit_scale, const float* dtab,
+                 const float* dalpha, float* dpre_ws, float* g_w1, float* g_b1, float* g_w2, float* g_ls, int ws, int heads,
+                 void* stream) {
+  return scot_cpb_bwd_launch(w1, b1, w2, logit_scale, dtab, dalpha, dpre_ws, g_w1, g_b1, g_w2, g_ls, ws, heads,
+                             (cudaStream_t)stream);
+}
+int scot_attn_fwd(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, int batch, int res, int ws,
+                  int shift, int heads, int head_dim, void* stream) {
+  return scot_attn_fwd_launch(qkv, out, lse, tab2, alpha, batch, res, ws, shift, heads, head_dim, (cudaStream_t)stream);
+}
+int scot_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, const float* tab2, const float* alpha,
+                  void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha, float* g_qbias,
+                  float* g_vbias, int batch, int res, int ws, int shift, int heads, int head_dim, void* stream) {
+  return scot_attn_bwd_launch(qkv, o, d_o, lse, tab2, alpha, dqkv, partial, partial_bytes, dtab, dalpha, g_qbias, g_vbias,
+                              batch, res, ws, shift, heads, head_dim, (cudaStream_t)stream);
+}
+
 }  // extern "C"

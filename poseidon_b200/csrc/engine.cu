@@ -1,0 +1,782 @@
+// Whole-model forward / backward sequencing for scOT (the native "runtime" of this repo).
+//
+// Mirrors the structure of ScOT.forward (scOT/model.py:1318-1509): embeddings -> encoder stages with patch
+// merging -> ConvNeXt blocks on the skips -> decoder stages with patch unmerging -> patch recovery -> loss,
+// and the hand-derived reverse pass. All device memory (parameters, gradients,
+// workspace arena) belongs to the caller; the engine object only holds host-side plans (offsets), so one
+// forward+backward is a fixed sequence of kernel launches on the caller's stream and can be captured in
+// a CUDA graph.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "internal.h"
+#include "scot_b200.h"
+
+namespace {
+
+struct ParamInfo {
+  std::string name;
+  long offset;
+  long numel;
+  int ndim;
+  long shape[4];
+};
+
+struct NormP {
+  long ww = -1, wb = -1, bw = -1, bb = -1;  // conditioned: weight.weight, weight.bias, bias.weight, bias.bias
+};                                           // plain LayerNorm: wb = weight, bb = bias, ww = bw = -1
+struct BlockP {
+  long wqkv, bqkv, ls, cw1, cb1, cw2, wo, bo, w1, b1, w2, b2;
+  NormP ln1, ln2;
+};
+struct MergeP { long wred; NormP norm; };
+struct UnmergeP { long wup, wmix; NormP norm; };
+struct CnxP { long gamma, wdw, bdw, w1, b1, w2, b2; NormP norm; };
+
+struct Geo {
+  int res, C, heads, hd, ws, shift, depth;
+  long M;  // batch * res * res
+};
+
+// offsets (bytes) into the caller's arena
+struct BlockBuf {
+  size_t qkv, o, lse, zhat1, rstd1, y1b, h, g, zhat2, rstd2, xout, xbout, tab2, alpha, dtab, dalpha;
+};
+struct NormBuf { size_t zhat, rstd; };
+struct CnxBuf { size_t nb, h, g, z2b, out, zhat, rstd; };
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) & ~size_t(255);
+    return o;
+  }
+};
+
+}  // namespace
+
+struct ScotEngine {
+  ScotModelDesc d;
+  int batch;
+  int ns;
+  int hidden_mult_num;  // mlp hidden = int(mlp_ratio * C)
+  std::vector<Geo> geo;
+  std::vector<ParamInfo> params;
+  long n_elems = 0;  // flat parameter buffer length (elements)
+  // parameter offsets
+  long emb_w, emb_b;
+  NormP emb_norm;
+  std::vector<std::vector<BlockP>> enc, dec;  // [stage][block] (dec indexed by decoder layer j)
+  std::vector<MergeP> merge;                  // [stage s] for s < ns-1
+  std::vector<UnmergeP> unmerge;              // [decoder layer j] valid when stage > 0
+  std::vector<std::vector<CnxP>> cnx;         // [stage][k]
+  long rec_w, rec_b, rec_mix;
+  // arena plan
+  size_t ws_bytes = 0;
+  size_t wb16;  // bf16 copy of the flat parameters
+  size_t p16, emb_zhat, emb_rstd, emb_x, emb_xb;
+  std::vector<std::vector<BlockBuf>> ebuf, dbuf;
+  std::vector<size_t> m_g16, m_x, m_xb;  // merge: gathered input (bf16), output fp32 / bf16
+  std::vector<NormBuf> m_norm, u_norm;
+  std::vector<size_t> u_nb, u_x, u_xb;   // unmerge: normalised (bf16), decoder stage input fp32 / bf16
+  std::vector<std::vector<CnxBuf>> cbuf;
+  std::vector<size_t> skip_xb;           // bf16 copy of the post-ConvNeXt skip of the last stage (if any)
+  size_t rec_bias, rec_D, pred_copy, loss_sums;
+  size_t z32, y32;                       // fp32 scratch [M0*C0] each
+  // backward scratch
+  size_t dzb, dqkv, dh, dob, partial, dpre, dpred, dD16, dgrads_zero_begin, dgrads_zero_bytes;
+  size_t partial_bytes;
+  std::vector<size_t> gstage;            // fp32 [M_s, C_s]
+  // forward state needed by backward
+  const float* last_pixels = nullptr;
+  const float* last_time = nullptr;
+  const float* last_labels = nullptr;
+  const uint8_t* last_mask = nullptr;
+  int last_mask_mode = 0;
+  float* last_pred = nullptr;
+  bool have_forward = false;
+};
+
+namespace {
+
+long align_up(long v, long a) { return (v + a - 1) / a * a; }
+
+struct Registry {
+  ScotEngine* e;
+  long cursor = 0;
+  long alloc(long numel, long align = 64) {
+    cursor = align_up(cursor, align);
+    const long o = cursor;
+    cursor += numel;
+    return o;
+  }
+  void reg(const std::string& name, long off, std::initializer_list<long> shape) {
+    ParamInfo p;
+    p.name = name;
+    p.offset = off;
+    p.ndim = (int)shape.size();
+    p.numel = 1;
+    int i = 0;
+    for (long s : shape) {
+      p.shape[i++] = s;
+      p.numel *= s;
+    }
+    for (; i < 4; ++i) p.shape[i] = 1;
+    e->params.push_back(p);
+  }
+  long add(const std::string& name, std::initializer_list<long> shape) {
+    long n = 1;
+    for (long s : shape) n *= s;
+    const long o = alloc(n);
+    reg(name, o, shape);
+    return o;
+  }
+  NormP norm(const std::string& pre, long C, bool cond) {
+    NormP n;
+    if (cond) {
+      n.ww = add(pre + ".weight.weight", {C, 1});
+      n.wb = add(pre + ".weight.bias", {C});
+      n.bw = add(pre + ".bias.weight", {C, 1});
+      n.bb = add(pre + ".bias.bias", {C});
+    } else {
+      n.wb = add(pre + ".weight", {C});
+      n.bb = add(pre + ".bias", {C});
+    }
+    return n;
+  }
+  BlockP block(const std::string& pre, long C, long heads, long hidden, bool cond) {
+    BlockP b;
+    const std::string a = pre + ".attention.self";
+    b.ls = add(a + ".logit_scale", {heads, 1, 1});
+    b.cw1 = add(a + ".continuous_position_bias_mlp.0.weight", {512, 2});
+    b.cb1 = add(a + ".continuous_position_bias_mlp.0.bias", {512});
+    b.cw2 = add(a + ".continuous_position_bias_mlp.2.weight", {heads, 512});
+    // q, k, v weights contiguous -> one [3C, C] GEMM operand
+    b.wqkv = alloc(3 * C * C);
+    reg(a + ".query.weight", b.wqkv, {C, C});
+    reg(a + ".key.weight", b.wqkv + C * C, {C, C});
+    reg(a + ".value.weight", b.wqkv + 2 * C * C, {C, C});
+    // [bq | zeros (key has no bias, HF:417) | bv] contiguous -> one [3C] epilogue bias
+    b.bqkv = alloc(3 * C);
+    reg(a + ".query.bias", b.bqkv, {C});
+    reg(a + ".value.bias", b.bqkv + 2 * C, {C});
+    b.wo = add(pre + ".attention.output.dense.weight", {C, C});
+    b.bo = add(pre + ".attention.output.dense.bias", {C});
+    b.ln1 = norm(pre + ".layernorm_before", C, cond);
+    b.w1 = add(pre + ".intermediate.dense.weight", {hidden, C});
+    b.b1 = add(pre + ".intermediate.dense.bias", {hidden});
+    b.w2 = add(pre + ".output.dense.weight", {C, hidden});
+    b.b2 = add(pre + ".output.dense.bias", {C});
+    b.ln2 = norm(pre + ".layernorm_after", C, cond);
+    return b;
+  }
+};
+
+long hidden_of(const ScotEngine* e, long C) { return (long)(e->d.mlp_ratio * (float)C); }
+
+int build_params(ScotEngine* e) {
+  const ScotModelDesc& d = e->d;
+  const bool cond = d.use_conditioning != 0;
+  Registry R{e};
+  const long C0 = d.embed_dim, ps = d.patch_size;
+  e->emb_w = R.add("embeddings.patch_embeddings.projection.weight", {C0, d.num_channels, ps, ps});
+  e->emb_b = R.add("embeddings.patch_embeddings.projection.bias", {C0});
+  e->emb_norm = R.norm("embeddings.norm", C0, cond);
+  e->enc.resize(e->ns);
+  e->merge.resize(e->ns);
+  for (int s = 0; s < e->ns; ++s) {
+    const Geo& g = e->geo[s];
+    for (int i = 0; i < g.depth; ++i)
+      e->enc[s].push_back(R.block("encoder.layers." + std::to_string(s) + ".blocks." + std::to_string(i), g.C, g.heads,
+                                  hidden_of(e, g.C), cond));
+    if (s < e->ns - 1) {
+      const std::string pre = "encoder.layers." + std::to_string(s) + ".downsample";
+      e->merge[s].wred = R.add(pre + ".reduction.weight", {2L * g.C, 4L * g.C});
+      e->merge[s].norm = R.norm(pre + ".norm", 2L * g.C, cond);
+    }
+  }
+  e->dec.resize(e->ns);
+  e->unmerge.resize(e->ns);
+  for (int j = 0; j < e->ns; ++j) {
+    const int s = e->ns - 1 - j;
+    const Geo& g = e->geo[s];
+    for (int i = 0; i < g.depth; ++i)
+      e->dec[j].push_back(R.block("decoder.layers." + std::to_string(j) + ".blocks." + std::to_string(i), g.C, g.heads,
+                                  hidden_of(e, g.C), cond));
+    if (s > 0) {
+      const std::string pre = "decoder.layers." + std::to_string(j) + ".upsample";
+      e->unmerge[j].wup = R.add(pre + ".upsample.weight", {2L * g.C, (long)g.C});
+      e->unmerge[j].wmix = R.add(pre + ".mixup.weight", {g.C / 2L, g.C / 2L});
+      e->unmerge[j].norm = R.norm(pre + ".norm", g.C / 2L, cond);
+    }
+  }
+  e->rec_w = R.add("patch_recovery.projection.weight", {C0, d.num_out_channels, ps, ps});
+  e->rec_b = R.add("patch_recovery.projection.bias", {d.num_out_channels});
+  e->rec_mix = R.add("patch_recovery.mixup.weight", {d.num_out_channels, d.num_out_channels, 5, 5});
+  e->cnx.resize(e->ns);
+  for (int s = 0; s < e->ns; ++s) {
+    const Geo& g = e->geo[s];
+    for (int k = 0; k < d.skip_blocks[s]; ++k) {
+      const std::string pre = "residual_blocks." + std::to_string(s) + "." + std::to_string(k);
+      CnxP c;
+      c.gamma = R.add(pre + ".weight", {(long)g.C});
+      c.wdw = R.add(pre + ".dwconv.weight", {(long)g.C, 1, 7, 7});
+      c.bdw = R.add(pre + ".dwconv.bias", {(long)g.C});
+      c.norm = R.norm(pre + ".norm", g.C, cond);
+      c.w1 = R.add(pre + ".pwconv1.weight", {4L * g.C, (long)g.C});
+      c.b1 = R.add(pre + ".pwconv1.bias", {4L * g.C});
+      c.w2 = R.add(pre + ".pwconv2.weight", {(long)g.C, 4L * g.C});
+      c.b2 = R.add(pre + ".pwconv2.bias", {(long)g.C});
+      e->cnx[s].push_back(c);
+    }
+  }
+  e->n_elems = align_up(R.cursor, 64);
+  return 0;
+}
+
+void plan_block(ScotEngine* e, Bump& b, BlockBuf& bb, const Geo& g) {
+  const size_t M = (size_t)g.M, C = (size_t)g.C, H = (size_t)hidden_of(e, g.C);
+  const size_t units = (size_t)e->batch * (g.res / g.ws) * (g.res / g.ws) * g.heads;
+  const size_t tabn = (size_t)(2 * g.ws - 1) * (2 * g.ws - 1) * g.heads;
+  bb.qkv = b.take(M * 3 * C * 2);
+  bb.o = b.take(M * C * 2);
+  bb.lse = b.take(units * g.ws * g.ws * 4);
+  bb.zhat1 = b.take(M * C * 2);
+  bb.rstd1 = b.take(M * 4);
+  bb.y1b = b.take(M * C * 2);
+  bb.h = b.take(M * H * 2);
+  bb.g = b.take(M * H * 2);
+  bb.zhat2 = b.take(M * C * 2);
+  bb.rstd2 = b.take(M * 4);
+  bb.xout = b.take(M * C * 4);
+  bb.xbout = b.take(M * C * 2);
+  bb.tab2 = b.take(tabn * 4);
+  bb.alpha = b.take((size_t)g.heads * 4);
+}
+
+int build_plan(ScotEngine* e) {
+  const ScotModelDesc& d = e->d;
+  Bump b;
+  const Geo& g0 = e->geo[0];
+  const size_t M0 = (size_t)g0.M, C0 = (size_t)g0.C;
+  const size_t K0 = (size_t)d.num_channels * d.patch_size * d.patch_size;
+  const size_t NR = (size_t)d.num_out_channels * d.patch_size * d.patch_size;
+  e->wb16 = b.take((size_t)e->n_elems * 2);
+  e->p16 = b.take(M0 * K0 * 2);
+  e->emb_zhat = b.take(M0 * C0 * 2);
+  e->emb_rstd = b.take(M0 * 4);
+  e->emb_x = b.take(M0 * C0 * 4);
+  e->emb_xb = b.take(M0 * C0 * 2);
+  e->ebuf.resize(e->ns);
+  e->dbuf.resize(e->ns);
+  e->m_g16.assign(e->ns, 0); e->m_x.assign(e->ns, 0); e->m_xb.assign(e->ns, 0);
+  e->m_norm.resize(e->ns); e->u_norm.resize(e->ns);
+  e->u_nb.assign(e->ns, 0); e->u_x.assign(e->ns, 0); e->u_xb.assign(e->ns, 0);
+  e->cbuf.resize(e->ns);
+  e->skip_xb.assign(e->ns, 0);
+  for (int s = 0; s < e->ns; ++s) {
+    const Geo& g = e->geo[s];
+    e->ebuf[s].resize(g.depth);
+    for (int i = 0; i < g.depth; ++i) plan_block(e, b, e->ebuf[s][i], g);
+    if (s < e->ns - 1) {
+      const Geo& gn = e->geo[s + 1];
+      e->m_g16[s] = b.take((size_t)gn.M * 4 * g.C * 2);
+      e->m_x[s] = b.take((size_t)gn.M * gn.C * 4);
+      e->m_xb[s] = b.take((size_t)gn.M * gn.C * 2);
+      e->m_norm[s].zhat = b.take((size_t)gn.M * gn.C * 2);
+      e->m_norm[s].rstd = b.take((size_t)gn.M * 4);
+    }
+    e->cbuf[s].resize(d.skip_blocks[s]);
+    for (int k = 0; k < d.skip_blocks[s]; ++k) {
+      CnxBuf& c = e->cbuf[s][k];
+      const size_t M = (size_t)g.M, C = (size_t)g.C;
+      c.nb = b.take(M * C * 2);
+      c.h = b.take(M * 4 * C * 2);
+      c.g = b.take(M * 4 * C * 2);
+      c.z2b = b.take(M * C * 2);
+      c.out = b.take(M * C * 4);
+      c.zhat = b.take(M * C * 2);
+      c.rstd = b.take(M * 4);
+    }
+    if (d.skip_blocks[s] > 0) e->skip_xb[s] = b.take((size_t)g.M * g.C * 2);
+  }
+  for (int j = 0; j < e->ns; ++j) {
+    const int s = e->ns - 1 - j;
+    const Geo& g = e->geo[s];
+    e->dbuf[j].resize(g.depth);
+    for (int i = 0; i < g.depth; ++i) plan_block(e, b, e->dbuf[j][i], g);
+    if (s > 0) {
+      const Geo& gf = e->geo[s - 1];  // finer stage
+      e->u_nb[j] = b.take((size_t)gf.M * gf.C * 2);
+      e->u_norm[j].zhat = b.take((size_t)gf.M * gf.C * 2);
+      e->u_norm[j].rstd = b.take((size_t)gf.M * 4);
+      e->u_x[j] = b.take((size_t)gf.M * gf.C * 4);
+      e->u_xb[j] = b.take((size_t)gf.M * gf.C * 2);
+    }
+  }
+  e->rec_bias = b.take(NR * 4);
+  e->rec_D = b.take(M0 * NR * 4);
+  e->loss_sums = b.take(64 * 4);
+  e->z32 = b.take(M0 * C0 * 4);
+  e->y32 = b.take(M0 * C0 * 4);
+  // ---- backward scratch ----
+  size_t max_h = 0;
+  for (int s = 0; s < e->ns; ++s) {
+    const size_t h = (size_t)e->geo[s].M * (size_t)hidden_of(e, e->geo[s].C);
+    const size_t h2 = (size_t)e->geo[s].M * 4 * e->geo[s].C;
+    max_h = h > max_h ? h : max_h;
+    max_h = h2 > max_h ? h2 : max_h;
+  }
+  e->dzb = b.take(M0 * C0 * 2);
+  e->dqkv = b.take(M0 * 3 * C0 * 2);
+  e->dh = b.take(max_h * 2);
+  e->dob = b.take(M0 * C0 * 2);
+  size_t pb = 0;
+  for (int s = 0; s < e->ns; ++s) {
+    const Geo& g = e->geo[s];
+    const size_t v = scot_attn_bwd_partial_bytes(g.ws, g.heads, e->batch * (g.res / g.ws) * (g.res / g.ws));
+    pb = v > pb ? v : pb;
+  }
+  e->partial_bytes = pb;
+  e->partial = b.take(pb);
+  e->dpre = b.take((size_t)31 * 31 * 32 * 4);
+  e->dpred = b.take((size_t)e->batch * d.num_out_channels * d.image_size * d.image_size * 4);
+  e->dD16 = b.take(M0 * NR * 2);
+  // per-layer bias-table gradient accumulators (zeroed at the start of every backward)
+  e->dgrads_zero_begin = b.off;
+  auto plan_dt = [&](BlockBuf& bb, const Geo& g) {
+    bb.dtab = b.take((size_t)(2 * g.ws - 1) * (2 * g.ws - 1) * g.heads * 4);
+    bb.dalpha = b.take((size_t)g.heads * 4);
+  };
+  for (int s = 0; s < e->ns; ++s)
+    for (auto& bb : e->ebuf[s]) plan_dt(bb, e->geo[s]);
+  for (int j = 0; j < e->ns; ++j)
+    for (auto& bb : e->dbuf[j]) plan_dt(bb, e->geo[e->ns - 1 - j]);
+  e->dgrads_zero_bytes = b.off - e->dgrads_zero_begin;
+  e->gstage.resize(e->ns);
+  for (int s = 0; s < e->ns; ++s) e->gstage[s] = b.take((size_t)e->geo[s].M * e->geo[s].C * 4);
+  e->ws_bytes = b.off;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// execution context helpers
+// ---------------------------------------------------------------------------------------------------
+struct Ctx {
+  ScotEngine* e;
+  const float* P;   // fp32 parameters
+  float* G;         // fp32 gradients (backward only)
+  uint8_t* A;       // arena
+  const float* time;
+  cudaStream_t st;
+  int impl;
+  template <typename T>
+  T* at(size_t off) const { return reinterpret_cast<T*>(A + off); }
+  const bf16* w16(long off) const { return reinterpret_cast<const bf16*>(A + e->wb16) + off; }
+  const float* p(long off) const { return off < 0 ? nullptr : P + off; }
+  float* g(long off) const { return off < 0 ? nullptr : G + off; }
+};
+
+#define RC(expr)                 \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+int gemm(const Ctx& c, const void* A, long lda, int amn, const void* B, long ldb, int bmn, long M, long N, long K, int mode,
+         const float* bias, void* out0, long ld0, void* out1 = nullptr, long ld1 = 0, const void* aux = nullptr,
+         long ldaux = 0, float* colsum = nullptr) {
+  ScotEpilogue ep{mode, bias, out0, ld0, out1, ld1, aux, ldaux, colsum};
+  return scot_gemm_launch(A, lda, amn, B, ldb, bmn, (int)M, (int)N, (int)K, &ep, c.impl, c.st);
+}
+
+int norm_fwd(const Ctx& c, const NormP& n, const float* z, const float* residual, float* x_out, void* xb_out, void* zhat,
+             float* rstd, long rows, int C, int rows_per_sample, int perm_res, float eps) {
+  return scot_cln_fwd_launch(z, residual, n.ww >= 0 ? c.time : nullptr, c.p(n.ww), c.p(n.wb), c.p(n.bw), c.p(n.bb), x_out,
+                             xb_out, zhat, rstd, rows, C, rows_per_sample, perm_res, eps, c.st);
+}
+int norm_bwd(const Ctx& c, const NormP& n, const float* dy, const void* zhat, const float* rstd, void* dz, int dz_f32,
+             float* g_bias_prev, long rows, int C, int rows_per_sample, int perm_res) {
+  return scot_cln_bwd_launch(dy, zhat, rstd, n.ww >= 0 ? c.time : nullptr, c.p(n.ww), c.p(n.wb), dz, dz_f32, c.g(n.ww),
+                             c.g(n.wb), c.g(n.bw), c.g(n.bb), g_bias_prev, rows, C, rows_per_sample, perm_res, c.st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ScOTLayer forward / backward (scOT/model.py:500-581)
+// ---------------------------------------------------------------------------------------------------
+int block_fwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, int shift, const float* x_in,
+              const bf16* xb_in) {
+  const ScotEngine* e = c.e;
+  const long M = g.M, C = g.C, H = hidden_of(e, g.C);
+  const int T = g.res * g.res;
+  RC(gemm(c, xb_in, C, 0, c.w16(p.wqkv), C, 0, M, 3 * C, C, SCOT_EPI_BF16, c.p(p.bqkv), c.at<bf16>(b.qkv), 3 * C));
+  RC(scot_attn_fwd_launch(c.at<bf16>(b.qkv), c.at<bf16>(b.o), c.at<float>(b.lse), c.at<float>(b.tab2), c.at<float>(b.alpha),
+                          e->batch, g.res, g.ws, shift, g.heads, g.hd, c.st));
+  RC(gemm(c, c.at<bf16>(b.o), C, 0, c.w16(p.wo), C, 0, M, C, C, SCOT_EPI_F32, c.p(p.bo), c.at<float>(e->z32), C));
+  RC(norm_fwd(c, p.ln1, c.at<float>(e->z32), x_in, c.at<float>(e->y32), c.at<bf16>(b.y1b), c.at<bf16>(b.zhat1),
+              c.at<float>(b.rstd1), M, (int)C, T, 0, e->d.layer_norm_eps));
+  RC(gemm(c, c.at<bf16>(b.y1b), C, 0, c.w16(p.w1), C, 0, M, H, C, SCOT_EPI_GELU, c.p(p.b1), c.at<bf16>(b.h), H,
+          c.at<bf16>(b.g), H));
+  RC(gemm(c, c.at<bf16>(b.g), H, 0, c.w16(p.w2), H, 0, M, C, H, SCOT_EPI_F32, c.p(p.b2), c.at<float>(e->z32), C));
+  RC(norm_fwd(c, p.ln2, c.at<float>(e->z32), c.at<float>(e->y32), c.at<float>(b.xout), c.at<bf16>(b.xbout),
+              c.at<bf16>(b.zhat2), c.at<float>(b.rstd2), M, (int)C, T, 0, e->d.layer_norm_eps));
+  return 0;
+}
+
+// g: gradient wrt the block output on entry, wrt the block input on exit (fp32, in place)
+int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, int shift, float* gr, const bf16* xb_in) {
+  const ScotEngine* e = c.e;
+  const long M = g.M, C = g.C, H = hidden_of(e, g.C);
+  const int T = g.res * g.res;
+  bf16* dzb = c.at<bf16>(e->dzb);
+  bf16* dh = c.at<bf16>(e->dh);
+  // y = y1 + LN2(mlp(y1))
+  RC(norm_bwd(c, p.ln2, gr, c.at<bf16>(b.zhat2), c.at<float>(b.rstd2), dzb, 0, c.g(p.b2), M, (int)C, T, 0));
+  RC(gemm(c, dzb, C, 1, c.at<bf16>(b.g), H, 1, C, H, M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.w2), H));
+  RC(gemm(c, dzb, C, 0, c.w16(p.w2), H, 1, M, H, C, SCOT_EPI_GELU_BWD, nullptr, dh, H, nullptr, 0, c.at<bf16>(b.h), H,
+          c.g(p.b1)));
+  RC(gemm(c, dh, H, 1, c.at<bf16>(b.y1b), C, 1, H, C, M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.w1), C));
+  RC(gemm(c, dh, H, 0, c.w16(p.w1), C, 1, M, C, H, SCOT_EPI_RMW_F32, nullptr, gr, C));
+  // y1 = x + LN1(attn(x))
+  RC(norm_bwd(c, p.ln1, gr, c.at<bf16>(b.zhat1), c.at<float>(b.rstd1), dzb, 0, c.g(p.bo), M, (int)C, T, 0));
+  RC(gemm(c, dzb, C, 1, c.at<bf16>(b.o), C, 1, C, C, M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.wo), C));
+  bf16* dob = c.at<bf16>(e->dob);
+  RC(gemm(c, dzb, C, 0, c.w16(p.wo), C, 1, M, C, C, SCOT_EPI_BF16, nullptr, dob, C));
+  bf16* dqkv = c.at<bf16>(e->dqkv);
+  RC(scot_attn_bwd_launch(c.at<bf16>(b.qkv), c.at<bf16>(b.o), dob, c.at<float>(b.lse), c.at<float>(b.tab2),
+                          c.at<float>(b.alpha), dqkv, c.at<float>(e->partial), e->partial_bytes, c.at<float>(b.dtab),
+                          c.at<float>(b.dalpha), c.g(p.bqkv), c.g(p.bqkv + 2 * C), e->batch, g.res, g.ws, shift, g.heads,
+                          g.hd, c.st));
+  RC(gemm(c, dqkv, 3 * C, 1, xb_in, C, 1, 3 * C, C, M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.wqkv), C));
+  RC(gemm(c, dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
+  RC(scot_cpb_bwd_launch(c.p(p.cw1), c.p(p.cb1), c.p(p.cw2), c.p(p.ls), c.at<float>(b.dtab), c.at<float>(b.dalpha),
+                         c.at<float>(e->dpre), c.g(p.cw1), c.g(p.cb1), c.g(p.cw2), c.g(p.ls), g.ws, g.heads, c.st));
+  return 0;
+}
+
+int shift_of(const Geo& g, int orig_index) { return (orig_index % 2 == 0) ? 0 : g.shift; }
+
+}  // namespace
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+extern "C" {
+
+int scot_engine_create(const ScotModelDesc* desc, int batch, ScotEngine** out) {
+  SCOT_REQUIRE(desc && out && batch > 0, "engine_create: bad arguments");
+  const ScotModelDesc& d = *desc;
+  SCOT_REQUIRE(d.num_stages >= 1 && d.num_stages <= 4, "engine_create: 1..4 stages supported (got %d)", d.num_stages);
+  SCOT_REQUIRE(d.image_size % d.patch_size == 0, "engine_create: image_size must be a multiple of patch_size");
+  SCOT_REQUIRE(d.mlp_ratio > 0.f, "engine_create: mlp_ratio");
+  SCOT_REQUIRE(d.num_out_channels * d.num_out_channels * 25 <= 1024, "engine_create: at most 6 output channels");
+  ScotEngine* e = new ScotEngine();
+  e->d = d;
+  e->batch = batch;
+  e->ns = d.num_stages;
+  const int grid = d.image_size / d.patch_size;
+  for (int s = 0; s < e->ns; ++s) {
+    Geo g;
+    g.res = grid >> s;
+    g.C = d.embed_dim << s;
+    g.heads = d.num_heads[s];
+    g.depth = d.depths[s];
+    if (g.res < 1 || (grid % (1 << s)) != 0 || g.C % g.heads != 0) {
+      delete e;
+      SCOT_REQUIRE(false, "engine_create: stage %d geometry invalid (res %d, C %d, heads %d)", s, g.res, g.C, g.heads);
+    }
+    g.hd = g.C / g.heads;
+    g.ws = g.res <= d.window_size ? g.res : d.window_size;        // scOT/model.py:428-430
+    g.shift = g.res <= g.ws ? 0 : d.window_size / 2;               // scOT/model.py:431-440
+    g.M = (long)batch * g.res * g.res;
+    const bool ok = (g.ws == 16 || g.ws == 8 || g.ws == 4) && (g.hd == 16 || g.hd == 32 || g.hd == 64) &&
+                    g.res % g.ws == 0 && g.C % 16 == 0 && (long)(d.mlp_ratio * g.C) % 16 == 0;
+    if (!ok) {
+      delete e;
+      SCOT_REQUIRE(false,
+                   "engine_create: stage %d unsupported (window %d must be 16/8/4, head_dim %d must be 16/32/64, res %d)", s,
+                   g.ws, g.hd, g.res);
+    }
+    e->geo.push_back(g);
+  }
+  build_params(e);
+  build_plan(e);
+  *out = e;
+  return 0;
+}
+
+void scot_engine_destroy(ScotEngine* e) { delete e; }
+
+long scot_engine_num_params(const ScotEngine* e) { return (long)e->params.size(); }
+long scot_engine_param_elems(const ScotEngine* e) { return e->n_elems; }
+size_t scot_engine_workspace_bytes(const ScotEngine* e) { return e->ws_bytes; }
+
+int scot_engine_param_info(const ScotEngine* e, long i, char* name, int name_cap, long* offset, long* numel, int* ndim,
+                           long* shape4) {
+  SCOT_REQUIRE(e && i >= 0 && i < (long)e->params.size(), "param_info: index out of range");
+  const ParamInfo& p = e->params[i];
+  if (name && name_cap > 0) {
+    strncpy(name, p.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (offset) *offset = p.offset;
+  if (numel) *numel = p.numel;
+  if (ndim) *ndim = p.ndim;
+  if (shape4)
+    for (int k = 0; k < 4; ++k) shape4[k] = p.shape[k];
+  return 0;
+}
+
+int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const float* pixel_values, const float* time,
+                        const float* labels, const uint8_t* mask, int mask_mode, float* pred_out, float* loss_out,
+                        int gemm_impl, void* stream) {
+  SCOT_REQUIRE(e && params && arena && pixel_values && pred_out, "engine_forward: null pointer");
+  const ScotModelDesc& d = e->d;
+  SCOT_REQUIRE(!d.use_conditioning || time != nullptr, "engine_forward: time is required when use_conditioning=True");
+  SCOT_REQUIRE(labels == nullptr || loss_out != nullptr, "engine_forward: loss_out required with labels");
+  SCOT_REQUIRE(((uintptr_t)arena & 255) == 0 && ((uintptr_t)params & 15) == 0, "engine_forward: arena must be 256 B aligned");
+  Ctx c{e, params, nullptr, (uint8_t*)arena, time, (cudaStream_t)stream, gemm_impl};
+  const int B = e->batch, ns = e->ns;
+  const Geo& g0 = e->geo[0];
+  // bf16 copy of all parameters (GEMM operands)
+  RC(scot_cast_f32_bf16_launch(params, c.at<bf16>(e->wb16), e->n_elems, c.st));
+  // relative-position-bias tables for every attention layer (batch independent)
+  for (int s = 0; s < ns; ++s) {
+    for (int i = 0; i < e->geo[s].depth; ++i) {
+      const BlockP& p = e->enc[s][i];
+      const BlockBuf& b = e->ebuf[s][i];
+      RC(scot_cpb_fwd_launch(c.p(p.cw1), c.p(p.cb1), c.p(p.cw2), c.p(p.ls), c.at<float>(b.tab2), c.at<float>(b.alpha),
+                             e->geo[s].ws, e->geo[s].heads, c.st));
+      const BlockP& q = e->dec[ns - 1 - s][i];
+      const BlockBuf& bq = e->dbuf[ns - 1 - s][i];
+      RC(scot_cpb_fwd_launch(c.p(q.cw1), c.p(q.cb1), c.p(q.cw2), c.p(q.ls), c.at<float>(bq.tab2), c.at<float>(bq.alpha),
+                             e->geo[s].ws, e->geo[s].heads, c.st));
+    }
+  }
+  // ---- embeddings (scOT/model.py:295-310, 345-366) ----
+  const int K0 = d.num_channels * d.patch_size * d.patch_size;
+  RC(scot_im2col_patch_launch(pixel_values, c.at<bf16>(e->p16), B, d.num_channels, d.image_size, d.image_size, d.patch_size,
+                              c.st));
+  RC(gemm(c, c.at<bf16>(e->p16), K0, 0, c.w16(e->emb_w), K0, 0, g0.M, g0.C, K0, SCOT_EPI_F32, c.p(e->emb_b),
+          c.at<float>(e->z32), g0.C));
+  RC(norm_fwd(c, e->emb_norm, c.at<float>(e->z32), nullptr, c.at<float>(e->emb_x), c.at<bf16>(e->emb_xb),
+              c.at<bf16>(e->emb_zhat), c.at<float>(e->emb_rstd), g0.M, g0.C, g0.res * g0.res, 0, 1e-5f));
+  // ---- encoder (model.py:816-861) ----
+  const float* x = c.at<float>(e->emb_x);
+  const bf16* xb = c.at<bf16>(e->emb_xb);
+  std::vector<const float*> skip(ns);
+  std::vector<const bf16*> skipb(ns);
+  for (int s = 0; s < ns; ++s) {
+    const Geo& g = e->geo[s];
+    const float* stage_in = x;
+    for (int i = 0; i < g.depth; ++i) {
+      RC(block_fwd(c, e->enc[s][i], e->ebuf[s][i], g, shift_of(g, i), x, xb));
+      x = c.at<float>(e->ebuf[s][i].xout);
+      xb = c.at<bf16>(e->ebuf[s][i].xbout);
+    }
+    skip[s] = x;
+    skipb[s] = xb;
+    if (s < ns - 1) {
+      const Geo& gn = e->geo[s + 1];
+      RC(scot_merge_gather_launch(x, stage_in, c.at<bf16>(e->m_g16[s]), B, g.res, g.C, c.st));
+      RC(gemm(c, c.at<bf16>(e->m_g16[s]), 4L * g.C, 0, c.w16(e->merge[s].wred), 4L * g.C, 0, gn.M, gn.C, 4L * g.C,
+              SCOT_EPI_F32, nullptr, c.at<float>(e->z32), gn.C));
+      RC(norm_fwd(c, e->merge[s].norm, c.at<float>(e->z32), nullptr, c.at<float>(e->m_x[s]), c.at<bf16>(e->m_xb[s]),
+                  c.at<bf16>(e->m_norm[s].zhat), c.at<float>(e->m_norm[s].rstd), gn.M, gn.C, gn.res * gn.res, 0, 1e-5f));
+      x = c.at<float>(e->m_x[s]);
+      xb = c.at<bf16>(e->m_xb[s]);
+    }
+  }
+  // ---- ConvNeXt blocks on the skips (model.py:198-217, 1388-1393) ----
+  for (int s = 0; s < ns; ++s) {
+    const Geo& g = e->geo[s];
+    for (int k = 0; k < d.skip_blocks[s]; ++k) {
+      const CnxP& p = e->cnx[s][k];
+      const CnxBuf& b = e->cbuf[s][k];
+      RC(scot_dwconv7_fwd_launch(skip[s], c.p(p.wdw), c.p(p.bdw), c.at<float>(e->z32), B, g.res, g.C, c.st));
+      RC(norm_fwd(c, p.norm, c.at<float>(e->z32), nullptr, nullptr, c.at<bf16>(b.nb), c.at<bf16>(b.zhat),
+                  c.at<float>(b.rstd), g.M, g.C, g.res * g.res, 0, d.layer_norm_eps));
+      RC(gemm(c, c.at<bf16>(b.nb), g.C, 0, c.w16(p.w1), g.C, 0, g.M, 4L * g.C, g.C, SCOT_EPI_GELU, c.p(p.b1),
+              c.at<bf16>(b.h), 4L * g.C, c.at<bf16>(b.g), 4L * g.C));
+      RC(gemm(c, c.at<bf16>(b.g), 4L * g.C, 0, c.w16(p.w2), 4L * g.C, 0, g.M, g.C, 4L * g.C, SCOT_EPI_F32, c.p(p.b2),
+              c.at<float>(e->z32), g.C));
+      RC(scot_scale_add_fwd_launch(skip[s], c.at<float>(e->z32), c.p(p.gamma), c.at<float>(b.out), c.at<bf16>(b.z2b), g.M,
+                                   g.C, c.st));
+      skip[s] = c.at<float>(b.out);
+    }
+    if (d.skip_blocks[s] > 0 && s == ns - 1) {
+      RC(scot_cast_f32_bf16_launch(skip[s], c.at<bf16>(e->skip_xb[s]), g.M * g.C, c.st));
+      skipb[s] = c.at<bf16>(e->skip_xb[s]);
+    }
+  }
+  // ---- decoder (model.py:916-961, 1145-1240) ----
+  x = skip[ns - 1];
+  xb = skipb[ns - 1];
+  for (int j = 0; j < ns; ++j) {
+    const int s = ns - 1 - j;
+    const Geo& g = e->geo[s];
+    for (int bi = 0; bi < g.depth; ++bi) {
+      const int orig = g.depth - 1 - bi;  // blocks are stored in reversed construction order (model.py:900)
+      RC(block_fwd(c, e->dec[j][bi], e->dbuf[j][bi], g, shift_of(g, orig), x, xb));
+      x = c.at<float>(e->dbuf[j][bi].xout);
+      xb = c.at<bf16>(e->dbuf[j][bi].xbout);
+    }
+    if (s > 0) {
+      const Geo& gf = e->geo[s - 1];
+      const UnmergeP& p = e->unmerge[j];
+      RC(gemm(c, xb, g.C, 0, c.w16(p.wup), g.C, 0, g.M, 2L * g.C, g.C, SCOT_EPI_F32, nullptr, c.at<float>(e->z32),
+              2L * g.C));
+      RC(norm_fwd(c, p.norm, c.at<float>(e->z32), nullptr, nullptr, c.at<bf16>(e->u_nb[j]), c.at<bf16>(e->u_norm[j].zhat),
+                  c.at<float>(e->u_norm[j].rstd), gf.M, gf.C, gf.res * gf.res, g.res, 1e-5f));
+      RC(gemm(c, c.at<bf16>(e->u_nb[j]), gf.C, 0, c.w16(p.wmix), gf.C, 0, gf.M, gf.C, gf.C, SCOT_EPI_ADD_F32_BF16, nullptr,
+              c.at<float>(e->u_x[j]), gf.C, c.at<bf16>(e->u_xb[j]), gf.C, skip[s - 1], gf.C));
+      x = c.at<float>(e->u_x[j]);
+      xb = c.at<bf16>(e->u_xb[j]);
+    }
+  }
+  // ---- patch recovery (model.py:639-647) ----
+  const int NR = d.num_out_channels * d.patch_size * d.patch_size;
+  RC(scot_expand_bias_launch(c.p(e->rec_b), c.at<float>(e->rec_bias), NR, d.patch_size * d.patch_size, c.st));
+  RC(gemm(c, xb, g0.C, 0, c.w16(e->rec_w), NR, 1, g0.M, NR, g0.C, SCOT_EPI_F32, c.at<float>(e->rec_bias),
+          c.at<float>(e->rec_D), NR));
+  const float* resid = d.learn_residual ? pixel_values : nullptr;
+  RC(scot_conv5_fwd_launch(c.at<float>(e->rec_D), c.p(e->rec_mix), resid, d.num_channels, labels, mask,
+                           labels ? mask_mode : 0, pred_out, B, d.num_out_channels, d.image_size, d.image_size,
+                           d.patch_size, c.st));
+  if (labels != nullptr) {
+    RC(scot_loss_fwd_launch(pred_out, labels, c.at<float>(e->loss_sums), loss_out, d.n_slices >= 2 ? d.slices : nullptr,
+                            d.n_slices, d.loss_p, B, d.num_out_channels, (long)d.image_size * d.image_size, c.st));
+  }
+  e->last_pixels = pixel_values;
+  e->last_time = time;
+  e->last_labels = labels;
+  e->last_mask = mask;
+  e->last_mask_mode = labels ? mask_mode : 0;
+  e->last_pred = pred_out;
+  e->have_forward = true;
+  return 0;
+}
+
+int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void* arena, const float* grad_loss,
+                         const float* grad_pred, int gemm_impl, void* stream) {
+  SCOT_REQUIRE(e && params && grads && arena, "engine_backward: null pointer");
+  SCOT_REQUIRE(e->have_forward, "engine_backward: call scot_engine_forward first");
+  SCOT_REQUIRE(grad_loss != nullptr || grad_pred != nullptr, "engine_backward: need grad_loss and/or grad_pred");
+  SCOT_REQUIRE(grad_loss == nullptr || e->last_labels != nullptr, "engine_backward: grad_loss given but forward had no labels");
+  const ScotModelDesc& d = e->d;
+  Ctx c{e, params, grads, (uint8_t*)arena, e->last_time, (cudaStream_t)stream, gemm_impl};
+  const int B = e->batch, ns = e->ns;
+  const Geo& g0 = e->geo[0];
+  const int NR = d.num_out_channels * d.patch_size * d.patch_size;
+  const long HW = (long)d.image_size * d.image_size;
+  SCOT_CHECK_CUDA(cudaMemsetAsync(c.at<uint8_t>(e->dgrads_zero_begin), 0, e->dgrads_zero_bytes, c.st));
+  // ---- loss + patch recovery backward ----
+  float* dpred = c.at<float>(e->dpred);
+  RC(scot_loss_bwd_launch(e->last_pred, e->last_labels, c.at<float>(e->loss_sums), grad_loss, grad_pred, e->last_mask,
+                          e->last_mask_mode, dpred, d.n_slices >= 2 ? d.slices : nullptr, d.n_slices, d.loss_p, B,
+                          d.num_out_channels, HW, c.st));
+  RC(scot_conv5_bwd_launch(c.at<float>(e->rec_D), c.p(e->rec_mix), dpred, c.at<bf16>(e->dD16), c.g(e->rec_mix),
+                           c.g(e->rec_b), B, d.num_out_channels, d.image_size, d.image_size, d.patch_size, c.st));
+  // final decoder output (bf16) = input of the recovery GEMM
+  const BlockBuf& lastb = e->dbuf[ns - 1].back();
+  const bf16* xb_final = c.at<bf16>(lastb.xbout);
+  RC(gemm(c, xb_final, g0.C, 1, c.at<bf16>(e->dD16), NR, 1, g0.C, NR, g0.M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(e->rec_w), NR));
+  RC(gemm(c, c.at<bf16>(e->dD16), NR, 0, c.w16(e->rec_w), NR, 0, g0.M, g0.C, NR, SCOT_EPI_F32, nullptr,
+          c.at<float>(e->gstage[0]), g0.C));
+  // ---- decoder backward (finest stage first) ----
+  for (int j = ns - 1; j >= 0; --j) {
+    const int s = ns - 1 - j;
+    const Geo& g = e->geo[s];
+    float* gr = c.at<float>(e->gstage[s]);
+    for (int bi = g.depth - 1; bi >= 0; --bi) {
+      const int orig = g.depth - 1 - bi;
+      const bf16* xb_in;
+      if (bi > 0) xb_in = c.at<bf16>(e->dbuf[j][bi - 1].xbout);
+      else if (j == 0) xb_in = (d.skip_blocks[s] > 0) ? c.at<bf16>(e->skip_xb[s]) : c.at<bf16>(e->ebuf[s].back().xbout);
+      else xb_in = c.at<bf16>(e->u_xb[j - 1]);
+      RC(block_bwd(c, e->dec[j][bi], e->dbuf[j][bi], g, shift_of(g, orig), gr, xb_in));
+    }
+    if (j > 0) {
+      // gr = grad wrt (mixup(norm(shuffle(upsample(x_coarse)))) + skip[s]); the skip part stays in gstage[s]
+      const int jc = j - 1;  // decoder layer that produced this stage's input
+      const Geo& gc = e->geo[s + 1];
+      const UnmergeP& p = e->unmerge[jc];
+      bf16* gb = c.at<bf16>(e->dzb);
+      RC(scot_cast_f32_bf16_launch(gr, gb, g.M * g.C, c.st));
+      RC(gemm(c, gb, g.C, 1, c.at<bf16>(e->u_nb[jc]), g.C, 1, g.C, g.C, g.M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.wmix), g.C));
+      RC(gemm(c, gb, g.C, 0, c.w16(p.wmix), g.C, 1, g.M, g.C, g.C, SCOT_EPI_F32, nullptr, c.at<float>(e->z32), g.C));
+      bf16* du = c.at<bf16>(e->dh);  // [M_coarse, 2*C_coarse]
+      RC(norm_bwd(c, p.norm, c.at<float>(e->z32), c.at<bf16>(e->u_norm[jc].zhat), c.at<float>(e->u_norm[jc].rstd), du, 0,
+                  nullptr, g.M, g.C, g.res * g.res, gc.res));
+      const bf16* xb_coarse = c.at<bf16>(e->dbuf[jc].back().xbout);
+      RC(gemm(c, du, 2L * gc.C, 1, xb_coarse, gc.C, 1, 2L * gc.C, gc.C, gc.M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.wup), gc.C));
+      RC(gemm(c, du, 2L * gc.C, 0, c.w16(p.wup), gc.C, 1, gc.M, gc.C, 2L * gc.C, SCOT_EPI_F32, nullptr,
+              c.at<float>(e->gstage[s + 1]), gc.C));
+    }
+  }
+  // ---- ConvNeXt backward on every skip ----
+  for (int s = 0; s < ns; ++s) {
+    const Geo& g = e->geo[s];
+    float* gr = c.at<float>(e->gstage[s]);
+    for (int k = d.skip_blocks[s] - 1; k >= 0; --k) {
+      const CnxP& p = e->cnx[s][k];
+      const CnxBuf& b = e->cbuf[s][k];
+      const float* blk_in = (k == 0) ? c.at<float>(e->ebuf[s].back().xout) : c.at<float>(e->cbuf[s][k - 1].out);
+      bf16* dzb = c.at<bf16>(e->dzb);
+      bf16* dh = c.at<bf16>(e->dh);
+      RC(scot_scale_add_bwd_launch(gr, c.at<bf16>(b.z2b), c.p(p.gamma), dzb, c.g(p.gamma), c.g(p.b2), g.M, g.C, c.st));
+      RC(gemm(c, dzb, g.C, 1, c.at<bf16>(b.g), 4L * g.C, 1, g.C, 4L * g.C, g.M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.w2),
+              4L * g.C));
+      RC(gemm(c, dzb, g.C, 0, c.w16(p.w2), 4L * g.C, 1, g.M, 4L * g.C, g.C, SCOT_EPI_GELU_BWD, nullptr, dh, 4L * g.C, nullptr,
+              0, c.at<bf16>(b.h), 4L * g.C, c.g(p.b1)));
+      RC(gemm(c, dh, 4L * g.C, 1, c.at<bf16>(b.nb), g.C, 1, 4L * g.C, g.C, g.M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.w1), g.C));
+      RC(gemm(c, dh, 4L * g.C, 0, c.w16(p.w1), g.C, 1, g.M, g.C, 4L * g.C, SCOT_EPI_F32, nullptr, c.at<float>(e->z32), g.C));
+      RC(norm_bwd(c, p.norm, c.at<float>(e->z32), c.at<bf16>(b.zhat), c.at<float>(b.rstd), c.at<float>(e->y32), 1,
+                  c.g(p.bdw), g.M, g.C, g.res * g.res, 0));
+      RC(scot_dwconv7_bwd_launch(blk_in, c.p(p.wdw), c.at<float>(e->y32), gr, gr, c.g(p.wdw), B, g.res, g.C, c.st));
+    }
+  }
+  // ---- encoder backward (coarsest stage first) ----
+  for (int s = ns - 1; s >= 0; --s) {
+    const Geo& g = e->geo[s];
+    float* gr = c.at<float>(e->gstage[s]);
+    if (s < ns - 1) {
+      // merge backward: gstage[s+1] = grad wrt merge output
+      const Geo& gn = e->geo[s + 1];
+      const MergeP& p = e->merge[s];
+      bf16* dzb = c.at<bf16>(e->dzb);
+      RC(norm_bwd(c, p.norm, c.at<float>(e->gstage[s + 1]), c.at<bf16>(e->m_norm[s].zhat), c.at<float>(e->m_norm[s].rstd),
+                  dzb, 0, nullptr, gn.M, gn.C, gn.res * gn.res, 0));
+      RC(gemm(c, dzb, gn.C, 1, c.at<bf16>(e->m_g16[s]), 4L * g.C, 1, gn.C, 4L * g.C, gn.M, SCOT_EPI_ATOMIC_F32, nullptr,
+              c.g(p.wred), 4L * g.C));
+      RC(gemm(c, dzb, gn.C, 0, c.w16(p.wred), 4L * g.C, 1, gn.M, 4L * g.C, gn.C, SCOT_EPI_F32, nullptr, c.at<float>(e->z32),
+              4L * g.C));
+      RC(scot_merge_scatter_launch(c.at<float>(e->z32), gr, gr, B, g.res, g.C, c.st));
+    }
+    for (int i = g.depth - 1; i >= 0; --i) {
+      const bf16* xb_in;
+      if (i > 0) xb_in = c.at<bf16>(e->ebuf[s][i - 1].xbout);
+      else if (s == 0) xb_in = c.at<bf16>(e->emb_xb);
+      else xb_in = c.at<bf16>(e->m_xb[s - 1]);
+      RC(block_bwd(c, e->enc[s][i], e->ebuf[s][i], g, shift_of(g, i), gr, xb_in));
+    }
+    if (s < ns - 1) {
+      // the stage input also feeds the merge through `hidden + inputs` (model.py:847-849)
+      RC(scot_merge_scatter_launch(c.at<float>(e->z32), gr, gr, B, g.res, g.C, c.st));
+    }
+  }
+  // ---- embeddings backward ----
+  {
+    const int K0 = d.num_channels * d.patch_size * d.patch_size;
+    bf16* dzb = c.at<bf16>(e->dzb);
+    RC(norm_bwd(c, e->emb_norm, c.at<float>(e->gstage[0]), c.at<bf16>(e->emb_zhat), c.at<float>(e->emb_rstd), dzb, 0,
+                c.g(e->emb_b), g0.M, g0.C, g0.res * g0.res, 0));
+    RC(gemm(c, dzb, g0.C, 1, c.at<bf16>(e->p16), K0, 1, g0.C, K0, g0.M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(e->emb_w), K0));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -5,3 +5,48 @@
 
 int scot_gemm_launch(const void* A, long lda, int a_mn_major, const void* B, long ldb, int b_mn_major, int M, int N,
                      int K, const ScotEpilogue* e, int impl, cudaStream_t stream);
+
+// norm.cu
+int scot_cln_fwd_launch(const float* z, const float* residual, const float* time, const float* aw, const float* ab,
+                        const float* cw, const float* cb, float* x_out, void* xb_out, void* zhat, float* rstd,
+                        long rows, int C, int rows_per_sample, int perm_res, float eps, cudaStream_t st);
+int scot_cln_bwd_launch(const float* dy, const void* zhat, const float* rstd, const float* time, const float* aw,
+                        const float* ab, void* dz, int dz_is_f32, float* g_aw, float* g_ab, float* g_cw, float* g_cb,
+                        float* g_bias_prev, long rows, int C, int rows_per_sample, int perm_res, cudaStream_t st);
+// attention.cu
+size_t scot_attn_bwd_partial_bytes(int ws, int heads, int total_windows);
+int scot_cpb_fwd_launch(const float* w1, const float* b1, const float* w2, const float* logit_scale, float* tab2,
+                        float* alpha, int ws, int heads, cudaStream_t st);
+int scot_cpb_bwd_launch(const float* w1, const float* b1, const float* w2, const float* logit_scale, const float* dtab,
+                        const float* dalpha, float* dpre_ws, float* g_w1, float* g_b1, float* g_w2, float* g_ls, int ws,
+                        int heads, cudaStream_t st);
+int scot_attn_fwd_launch(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, int batch,
+                         int res, int ws, int shift, int heads, int hd, cudaStream_t st);
+int scot_attn_bwd_launch(const void* qkv, const void* o, const void* d_o, const float* lse, const float* tab2,
+                         const float* alpha, void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha,
+                         float* g_qbias, float* g_vbias, int batch, int res, int ws, int shift, int heads, int hd,
+                         cudaStream_t st);
+// misc.cu
+int scot_cast_f32_bf16_launch(const float* in, void* out, long n, cudaStream_t st);
+int scot_expand_bias_launch(const float* bias, float* out, int n, int rep, cudaStream_t st);
+int scot_im2col_patch_launch(const float* x, void* out, int B, int Cin, int H, int W, int ps, cudaStream_t st);
+int scot_merge_gather_launch(const float* x, const float* inp, void* out, int B, int res, int C, cudaStream_t st);
+int scot_merge_scatter_launch(const float* dG, const float* g_in, float* g_out, int B, int res, int C, cudaStream_t st);
+int scot_scale_add_fwd_launch(const float* in, const float* z, const float* gamma, float* out, void* zb, long rows, int C,
+                              cudaStream_t st);
+int scot_scale_add_bwd_launch(const float* g, const void* zb, const float* gamma, void* dz, float* g_gamma, float* g_bias,
+                              long rows, int C, cudaStream_t st);
+int scot_dwconv7_fwd_launch(const float* x, const float* w, const float* bias, float* out, int B, int res, int C,
+                            cudaStream_t st);
+int scot_dwconv7_bwd_launch(const float* x, const float* w, const float* dout, const float* g_in, float* g_out, float* g_w,
+                            int B, int res, int C, cudaStream_t st);
+int scot_conv5_fwd_launch(const float* D, const float* w, const float* resid, int resid_channels, const float* labels,
+                          const uint8_t* mask, int mask_mode, float* pred, int B, int OC, int H, int W, int ps,
+                          cudaStream_t st);
+int scot_conv5_bwd_launch(const float* D, const float* w, const float* dpred, void* dD, float* g_w, float* g_bias, int B,
+                          int OC, int H, int W, int ps, cudaStream_t st);
+int scot_loss_fwd_launch(const float* pred, const float* labels, float* sums, float* loss, const int* slices_host,
+                         int n_slices, int p, int B, int OC, long HW, cudaStream_t st);
+int scot_loss_bwd_launch(const float* pred, const float* labels, const float* sums, const float* gscale, const float* extra,
+                         const uint8_t* mask, int mask_mode, float* dpred, const int* slices_host, int n_slices, int p, int B,
+                         int OC, long HW, cudaStream_t st);

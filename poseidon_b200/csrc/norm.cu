@@ -1,0 +1,316 @@
+// (Conditional) LayerNorm forward / backward, fused with the residual add, the bf16 down-cast for the next
+// GEMM, the pixel-shuffle row permutation of ScOTPatchUnmerging and the bias-gradient column sums.
+//
+// Reference: ConditionalLayerNorm.forward (scOT/model.py:150-160): mean, E[x^2]-mean^2, eps inside the
+// sqrt, weight/bias = Linear(1, C)(time); LayerNorm (model.py:135-140) when use_conditioning=False.
+// Call sites fused here: ScOTLayer res-post-norm adds (model.py:570,574), ScOTEmbeddings.norm (:352),
+// ScOTPatchMerging.norm (:710), ScOTPatchUnmerging permute+norm (:748-759), ConvNeXtBlock.norm (:208).
+// HBM-bound: one (sub-)warp per token row, 128-bit loads, shuffle reductions, row kept in registers.
+#include "common.cuh"
+#include "internal.h"
+
+namespace {
+
+struct ClnFwdArgs {
+  const float* z;        // [rows, C] input (row index = r_in)
+  const float* residual; // [rows, C] or null (row index = r_out)
+  const float* time;     // [B] or null
+  const float* aw;       // scale slope  (weight.weight) [C] or null
+  const float* ab;       // scale offset (weight.bias)   [C]
+  const float* cw;       // shift slope  (bias.weight)   [C] or null
+  const float* cb;       // shift offset (bias.bias)     [C]
+  float* x_out;          // fp32 [rows, C] or null
+  bf16* xb_out;          // bf16 [rows, C] or null
+  bf16* zhat;            // bf16 normalised input (saved for backward) or null
+  float* rstd;           // [rows] or null
+  long rows;
+  int C;
+  int rows_per_sample;   // of the OUTPUT row index
+  int perm_res;          // 0: r_out = r_in. >0: unmerge pixel shuffle with input grid perm_res x perm_res
+  float eps;
+};
+
+// r_in = ((b*res + i)*res + j)*4 + a*2 + c  ->  r_out = (b*2res + 2i+a)*2res + 2j+c   (model.py:748-754)
+__device__ __forceinline__ long unmerge_row(long r_in, int res) {
+  const int ac = (int)(r_in & 3);
+  const long m = r_in >> 2;
+  const int j = (int)(m % res);
+  const long t = m / res;
+  const int i = (int)(t % res);
+  const long b = t / res;
+  const int a = ac >> 1, c = ac & 1;
+  return (b * (2 * res) + 2 * i + a) * (long)(2 * res) + 2 * j + c;
+}
+
+template <int LPR, int V>
+__global__ void __launch_bounds__(256) cln_fwd_kernel(ClnFwdArgs p) {
+  constexpr int RPW = 32 / LPR;  // rows per warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const long warp_global = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long r_in = warp_global * RPW + sub;
+  if (r_in >= p.rows) return;  // whole sub-warp exits together; shuffles below use the sub-group mask only
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int nvec = p.C >> 2;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int cv = sl + i * LPR;
+    if (cv < nvec) {
+      v[i] = *reinterpret_cast<const float4*>(p.z + r_in * p.C + cv * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(mask, s, o);
+  const float mean = s / (float)p.C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int cv = sl + i * LPR;
+    if (cv < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(mask, q, o);
+  const float rstd = rsqrtf(q / (float)p.C + p.eps);
+  const long r_out = p.perm_res > 0 ? unmerge_row(r_in, p.perm_res) : r_in;
+  const float t = p.time != nullptr ? p.time[r_out / p.rows_per_sample] : 0.f;
+  if (sl == 0 && p.rstd != nullptr) p.rstd[r_out] = rstd;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int cv = sl + i * LPR;
+    if (cv >= nvec) continue;
+    const int c0 = cv * 4;
+    float zh[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+    if (p.zhat != nullptr) {
+      // the saved normalised value is the bf16-rounded one; use the same rounded value below so that the
+      // backward pass differentiates exactly the function the forward pass evaluated
+      uint2 o = make_uint2(pack_bf16x2(zh[0], zh[1]), pack_bf16x2(zh[2], zh[3]));
+      *reinterpret_cast<uint2*>(p.zhat + r_out * p.C + c0) = o;
+    }
+    const float4 ab = *reinterpret_cast<const float4*>(p.ab + c0);
+    const float4 cb = *reinterpret_cast<const float4*>(p.cb + c0);
+    float sc[4] = {ab.x, ab.y, ab.z, ab.w}, sh[4] = {cb.x, cb.y, cb.z, cb.w};
+    if (p.aw != nullptr) {
+      const float4 aw = *reinterpret_cast<const float4*>(p.aw + c0);
+      const float4 cw = *reinterpret_cast<const float4*>(p.cw + c0);
+      sc[0] = fmaf(aw.x, t, sc[0]); sc[1] = fmaf(aw.y, t, sc[1]); sc[2] = fmaf(aw.z, t, sc[2]); sc[3] = fmaf(aw.w, t, sc[3]);
+      sh[0] = fmaf(cw.x, t, sh[0]); sh[1] = fmaf(cw.y, t, sh[1]); sh[2] = fmaf(cw.z, t, sh[2]); sh[3] = fmaf(cw.w, t, sh[3]);
+    }
+    float y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y[k] = fmaf(sc[k], zh[k], sh[k]);
+    if (p.residual != nullptr) {
+      const float4 r = *reinterpret_cast<const float4*>(p.residual + r_out * p.C + c0);
+      y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
+    }
+    if (p.x_out != nullptr) *reinterpret_cast<float4*>(p.x_out + r_out * p.C + c0) = make_float4(y[0], y[1], y[2], y[3]);
+    if (p.xb_out != nullptr)
+      *reinterpret_cast<uint2*>(p.xb_out + r_out * p.C + c0) = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
+  }
+}
+
+struct ClnBwdArgs {
+  const float* dy;   // [rows, C] gradient wrt the LN output (row index r_out)
+  const bf16* zhat;  // [rows, C] (r_out)
+  const float* rstd; // [rows]    (r_out)
+  const float* time; // [B] or null
+  const float* aw;   // [C] or null
+  const float* ab;   // [C]
+  void* dz;          // [rows, C] gradient wrt the LN input (row index r_in); bf16 or fp32
+  int dz_is_f32;
+  float* g_aw;       // param grads (atomic accumulate); g_aw / g_cw may be null (unconditioned)
+  float* g_ab;
+  float* g_cw;
+  float* g_cb;
+  float* g_bias_prev; // [C] or null: += column sums of dz (bias of the Linear that produced the LN input)
+  long rows;
+  int C;
+  int rows_per_sample;
+  int rows_per_block; // divides rows_per_sample
+  int perm_res;
+};
+
+template <int LPR, int V>
+__global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
+  extern __shared__ float red[];  // [3][C]
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int sub = lane / LPR, sl = lane % LPR;
+  const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int nvec = p.C >> 2;
+  for (int i = threadIdx.x; i < 3 * p.C; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const long row_begin = (long)blockIdx.x * p.rows_per_block;
+  const float t = p.time != nullptr ? p.time[row_begin / p.rows_per_sample] : 0.f;
+
+  float4 sc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int cv = sl + i * LPR;
+    if (cv < nvec) {
+      sc[i] = *reinterpret_cast<const float4*>(p.ab + cv * 4);
+      if (p.aw != nullptr) {
+        const float4 aw = *reinterpret_cast<const float4*>(p.aw + cv * 4);
+        sc[i].x = fmaf(aw.x, t, sc[i].x); sc[i].y = fmaf(aw.y, t, sc[i].y);
+        sc[i].z = fmaf(aw.z, t, sc[i].z); sc[i].w = fmaf(aw.w, t, sc[i].w);
+      }
+    } else {
+      sc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float4 acc_a[V], acc_c[V], acc_b[V];  // sum dy*zhat, sum dy, sum dz
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc_a[i] = acc_c[i] = acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int rr = warp * RPW + sub; rr < p.rows_per_block; rr += nwarps * RPW) {
+    const long r_out = row_begin + rr;  // rows_per_block is a multiple of RPW so sub-warps stay converged
+    float4 dy[V], zh[V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int cv = sl + i * LPR;
+      if (cv < nvec) {
+        dy[i] = *reinterpret_cast<const float4*>(p.dy + r_out * p.C + cv * 4);
+        const uint2 zr = *reinterpret_cast<const uint2*>(p.zhat + r_out * p.C + cv * 4);
+        const float2 z01 = unpack_bf16x2(zr.x), z23 = unpack_bf16x2(zr.y);
+        zh[i] = make_float4(z01.x, z01.y, z23.x, z23.y);
+        acc_a[i].x += dy[i].x * zh[i].x; acc_a[i].y += dy[i].y * zh[i].y;
+        acc_a[i].z += dy[i].z * zh[i].z; acc_a[i].w += dy[i].w * zh[i].w;
+        acc_c[i].x += dy[i].x; acc_c[i].y += dy[i].y; acc_c[i].z += dy[i].z; acc_c[i].w += dy[i].w;
+        // dzhat = dy * scale
+        dy[i].x *= sc[i].x; dy[i].y *= sc[i].y; dy[i].z *= sc[i].z; dy[i].w *= sc[i].w;
+        s1 += (dy[i].x + dy[i].y) + (dy[i].z + dy[i].w);
+        s2 += (dy[i].x * zh[i].x + dy[i].y * zh[i].y) + (dy[i].z * zh[i].z + dy[i].w * zh[i].w);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(mask, s1, o);
+      s2 += __shfl_xor_sync(mask, s2, o);
+    }
+    const float m1 = s1 / (float)p.C, m2 = s2 / (float)p.C;
+    const float rstd = p.rstd[r_out];
+    long r_in = r_out;
+    if (p.perm_res > 0) {
+      // inverse of unmerge_row
+      const int w2 = 2 * p.perm_res;
+      const int x = (int)(r_out % w2);
+      const long tt = r_out / w2;
+      const int y = (int)(tt % w2);
+      const long b = tt / w2;
+      r_in = (((b * p.perm_res + (y >> 1)) * p.perm_res + (x >> 1)) << 2) + ((y & 1) << 1) + (x & 1);
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int cv = sl + i * LPR;
+      if (cv < nvec) {
+        float4 dz;
+        dz.x = (dy[i].x - m1 - zh[i].x * m2) * rstd;
+        dz.y = (dy[i].y - m1 - zh[i].y * m2) * rstd;
+        dz.z = (dy[i].z - m1 - zh[i].z * m2) * rstd;
+        dz.w = (dy[i].w - m1 - zh[i].w * m2) * rstd;
+        if (p.dz_is_f32) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dz) + r_in * p.C + cv * 4) = dz;
+        } else {
+          const uint2 o = make_uint2(pack_bf16x2(dz.x, dz.y), pack_bf16x2(dz.z, dz.w));
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.dz) + r_in * p.C + cv * 4) = o;
+          const float2 a = unpack_bf16x2(o.x), b = unpack_bf16x2(o.y);
+          dz = make_float4(a.x, a.y, b.x, b.y);
+        }
+        acc_b[i].x += dz.x; acc_b[i].y += dz.y; acc_b[i].z += dz.z; acc_b[i].w += dz.w;
+      }
+    }
+  }
+  // block reduction (smem atomics; a handful per thread) then one global atomic per column per array
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int cv = sl + i * LPR;
+    if (cv < nvec) {
+      const int c0 = cv * 4;
+      atomicAdd(&red[c0 + 0], acc_a[i].x); atomicAdd(&red[c0 + 1], acc_a[i].y);
+      atomicAdd(&red[c0 + 2], acc_a[i].z); atomicAdd(&red[c0 + 3], acc_a[i].w);
+      atomicAdd(&red[p.C + c0 + 0], acc_c[i].x); atomicAdd(&red[p.C + c0 + 1], acc_c[i].y);
+      atomicAdd(&red[p.C + c0 + 2], acc_c[i].z); atomicAdd(&red[p.C + c0 + 3], acc_c[i].w);
+      atomicAdd(&red[2 * p.C + c0 + 0], acc_b[i].x); atomicAdd(&red[2 * p.C + c0 + 1], acc_b[i].y);
+      atomicAdd(&red[2 * p.C + c0 + 2], acc_b[i].z); atomicAdd(&red[2 * p.C + c0 + 3], acc_b[i].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const float sa = red[c], scs = red[p.C + c], sb = red[2 * p.C + c];
+    atomicAdd(p.g_ab + c, sa);
+    atomicAdd(p.g_cb + c, scs);
+    if (p.g_aw != nullptr) {
+      atomicAdd(p.g_aw + c, sa * t);
+      atomicAdd(p.g_cw + c, scs * t);
+    }
+    if (p.g_bias_prev != nullptr) atomicAdd(p.g_bias_prev + c, sb);
+  }
+}
+
+template <int LPR, int V>
+int launch_fwd(const ClnFwdArgs& a, cudaStream_t st) {
+  constexpr int RPW = 32 / LPR;
+  const int warps = 8;
+  const long blocks = (a.rows + (long)warps * RPW - 1) / ((long)warps * RPW);
+  cln_fwd_kernel<LPR, V><<<(unsigned)blocks, warps * 32, 0, st>>>(a);
+  SCOT_LAUNCH_CHECK();
+  return 0;
+}
+template <int LPR, int V>
+int launch_bwd(const ClnBwdArgs& a, cudaStream_t st) {
+  const long blocks = a.rows / a.rows_per_block;
+  cln_bwd_kernel<LPR, V><<<(unsigned)blocks, 256, 3 * a.C * sizeof(float), st>>>(a);
+  SCOT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+#define CLN_DISPATCH(FN, ARGS)                                                     \
+  do {                                                                             \
+    const int nvec = (ARGS).C / 4;                                                 \
+    if (nvec <= 8) return FN<8, 1>(ARGS, st);                                      \
+    if (nvec <= 16) return FN<16, 1>(ARGS, st);                                    \
+    if (nvec <= 32) return FN<32, 1>(ARGS, st);                                    \
+    if (nvec <= 64) return FN<32, 2>(ARGS, st);                                    \
+    if (nvec <= 96) return FN<32, 3>(ARGS, st);                                    \
+    if (nvec <= 192) return FN<32, 6>(ARGS, st);                                   \
+    if (nvec <= 384) return FN<32, 12>(ARGS, st);                                  \
+    SCOT_REQUIRE(false, "layer norm: C=%d not supported (max 1536)", (ARGS).C);    \
+  } while (0)
+
+int scot_cln_fwd_launch(const float* z, const float* residual, const float* time, const float* aw, const float* ab,
+                        const float* cw, const float* cb, float* x_out, void* xb_out, void* zhat, float* rstd,
+                        long rows, int C, int rows_per_sample, int perm_res, float eps, cudaStream_t st) {
+  SCOT_REQUIRE(z && ab && cb, "cln_fwd: null pointer");
+  SCOT_REQUIRE(C % 4 == 0 && rows > 0 && rows_per_sample > 0, "cln_fwd: bad shape rows=%ld C=%d", rows, C);
+  SCOT_REQUIRE((aw == nullptr) == (cw == nullptr), "cln_fwd: aw/cw must both be given or both null");
+  SCOT_REQUIRE(aw == nullptr || time != nullptr, "cln_fwd: conditioned norm needs time");
+  SCOT_REQUIRE(perm_res == 0 || residual == nullptr, "cln_fwd: residual not supported with permutation");
+  ClnFwdArgs a{z, residual, time, aw, ab, cw, cb, x_out, (bf16*)xb_out, (bf16*)zhat, rstd, rows, C, rows_per_sample,
+               perm_res, eps};
+  CLN_DISPATCH(launch_fwd, a);
+}
+
+int scot_cln_bwd_launch(const float* dy, const void* zhat, const float* rstd, const float* time, const float* aw,
+                        const float* ab, void* dz, int dz_is_f32, float* g_aw, float* g_ab, float* g_cw, float* g_cb,
+                        float* g_bias_prev, long rows, int C, int rows_per_sample, int perm_res, cudaStream_t st) {
+  SCOT_REQUIRE(dy && zhat && rstd && ab && dz && g_ab && g_cb, "cln_bwd: null pointer");
+  SCOT_REQUIRE(C % 4 == 0 && rows > 0, "cln_bwd: bad shape");
+  SCOT_REQUIRE((aw == nullptr) == (g_aw == nullptr) && (g_aw == nullptr) == (g_cw == nullptr), "cln_bwd: aw/g_aw/g_cw mismatch");
+  SCOT_REQUIRE(aw == nullptr || time != nullptr, "cln_bwd: conditioned norm needs time");
+  int rpb = rows_per_sample < 64 ? rows_per_sample : 64;
+  SCOT_REQUIRE(rows_per_sample % rpb == 0 && rows % rpb == 0 && rpb % 4 == 0, "cln_bwd: rows_per_sample=%d unsupported",
+               rows_per_sample);
+  ClnBwdArgs a{dy, (const bf16*)zhat, rstd, time, aw, ab, dz, dz_is_f32, g_aw, g_ab, g_cw, g_cb, g_bias_prev, rows, C,
+               rows_per_sample, rpb, perm_res};
+  CLN_DISPATCH(launch_bwd, a);
+}
