@@ -32,7 +32,13 @@ def run(name, impl, ref_dtype=torch.float64):
     rep["loss"] = float(out.loss); rep["loss_ref"] = rec["loss"]
     rep["out_finite"] = bool(torch.isfinite(out.output).all())
     t0 = time.time()
-    out.loss.backward()
+    gen = torch.Generator().manual_seed(123)
+    G = torch.randn(out.output.shape, generator=gen)
+    if LIN:
+        # smooth objective <G, pred>: free of the sign() discontinuity of the L1 loss
+        out.output.backward(G.cuda())
+    else:
+        out.loss.backward()
     torch.cuda.synchronize()
     rep["bwd_s"] = time.time() - t0
     grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
@@ -43,7 +49,10 @@ def run(name, impl, ref_dtype=torch.float64):
     if not hasattr(ocfg, "layer_norm_eps"): ocfg.layer_norm_eps = 1e-5
     loss, pred = O.scot_forward(ocfg, wr, x.to(ref_dtype), t.to(ref_dtype) if cfg.use_conditioning else None, y.to(ref_dtype),
                                 pm if rec["mask_channels"] else None)
-    loss.backward()
+    if LIN:
+        (pred * G.to(ref_dtype)).sum().backward()
+    else:
+        loss.backward()
     rep["oracle_s"] = time.time() - t0
     rep["out_rel_vs_oracle"] = rel(out.output.cpu(), pred.detach())
     errs = {k: rel(grads[k], wr[k].grad) for k in grads}
@@ -60,6 +69,7 @@ def run(name, impl, ref_dtype=torch.float64):
     rep["grad_rel_by_kind"] = {k: max(v) for k, v in sorted(kinds.items())}
     return rep
 
+LIN = "--lin" in sys.argv
 names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["tiny"]
 impl = L.GEMM_SIMT if "--simt" in sys.argv else L.GEMM_TCGEN05
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -69,7 +79,7 @@ for n in names:
     except Exception as ex:
         import traceback
         rep = {"name": n, "exc": traceback.format_exc()[-3000:]}
-    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", f"model_check_{n}_{impl}.json"), "w"), indent=1)
+    json.dump(rep, open(os.path.join(ROOT, "gpurun_out", f"model_check_{n}_{impl}_{'lin' if LIN else 'loss'}.json"), "w"), indent=1)
     print(json.dumps({k: v for k, v in rep.items() if k != "grad_rel_by_kind"}, indent=1)[:6000], flush=True)
     if "grad_rel_by_kind" in rep:
         print("BY KIND:", json.dumps(rep["grad_rel_by_kind"], indent=0))
