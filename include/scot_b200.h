@@ -84,13 +84,23 @@ int scot_cln_bwd(const float* dy, const void* zhat, const float* rstd, const flo
                  const float* ab, void* dz, int dz_is_f32, float* g_aw, float* g_ab, float* g_cw, float* g_cb,
                  float* g_bias_prev, long rows, int C, int rows_per_sample, int perm_res, void* stream);
 
-/* continuous relative position bias (HF modeling_swinv2.py:450-460,489-510):
- * tab2[r,h] = 16*sigmoid(mlp(coords[r]))[h]*log2(e), alpha[h] = exp(min(logit_scale[h], ln 100)) */
-int scot_cpb_fwd(const float* w1, const float* b1, const float* w2, const float* logit_scale, float* tab2, float* alpha,
-                 int ws, int heads, void* stream);
-int scot_cpb_bwd(const float* w1, const float* b1, const float* w2, const float* logit_scale, const float* dtab,
-                 const float* dalpha, float* dpre_ws, float* g_w1, float* g_b1, float* g_w2, float* g_ls, int ws, int heads,
-                 void* stream);
+/* continuous relative position bias (HF modeling_swinv2.py:450-460,489-510), all attention layers in one launch:
+ * tab2[r,h] = 16*sigmoid(mlp(coords[r]))[h]*log2(e), alpha[h] = exp(min(logit_scale[h], ln 100)).
+ * Parameters are addressed by element offsets into the flat fp32 parameter (and gradient) buffer, the
+ * outputs by 256-byte-unit offsets into the caller's arena. */
+#define SCOT_CPB_MAX_LAYERS 64
+typedef struct ScotCpbLayer {
+  int w1, b1, w2, ls;            /* continuous_position_bias_mlp.0.{weight,bias}, .2.weight, logit_scale */
+  int tab2, alpha;               /* forward outputs: [(2ws-1)^2, heads] and [heads] floats */
+  int dtab, dalpha, dpre;        /* backward: inputs dtab/dalpha (from scot_attn_bwd), scratch dpre [(2ws-1)^2*heads] */
+  short ws, heads;
+} ScotCpbLayer;
+typedef struct ScotCpbTable {
+  int n;
+  ScotCpbLayer layer[SCOT_CPB_MAX_LAYERS];
+} ScotCpbTable;
+int scot_cpb_fwd(const ScotCpbTable* table, const float* params, void* arena, void* stream);
+int scot_cpb_bwd(const ScotCpbTable* table, const float* params, float* grads, void* arena, void* stream);
 /* shifted-window cosine attention (HF:421-487 + scOT/model.py:522-559) on qkv [tokens, 3C] bf16 */
 int scot_attn_fwd(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, int batch, int res, int ws,
                   int shift, int heads, int head_dim, void* stream);

@@ -100,15 +100,24 @@ class ScotModelDesc(C.Structure):
     ]
 
 
+class ScotCpbLayer(C.Structure):
+    _fields_ = [("w1", C.c_int), ("b1", C.c_int), ("w2", C.c_int), ("ls", C.c_int), ("tab2", C.c_int), ("alpha", C.c_int),
+                ("dtab", C.c_int), ("dalpha", C.c_int), ("dpre", C.c_int), ("ws", C.c_short), ("heads", C.c_short)]
+
+
+class ScotCpbTable(C.Structure):
+    _fields_ = [("n", C.c_int), ("layer", ScotCpbLayer * 64)]
+
+
 def _declare_engine(lib):
     vp, i, l, f = C.c_void_p, C.c_int, C.c_long, C.c_float
     lib.scot_cln_fwd.argtypes = [vp] * 11 + [l, i, i, i, f, vp]
     lib.scot_cln_fwd.restype = i
     lib.scot_cln_bwd.argtypes = [vp] * 7 + [i] + [vp] * 5 + [l, i, i, i, vp]
     lib.scot_cln_bwd.restype = i
-    lib.scot_cpb_fwd.argtypes = [vp] * 6 + [i, i, vp]
+    lib.scot_cpb_fwd.argtypes = [C.POINTER(ScotCpbTable), vp, vp, vp]
     lib.scot_cpb_fwd.restype = i
-    lib.scot_cpb_bwd.argtypes = [vp] * 11 + [i, i, vp]
+    lib.scot_cpb_bwd.argtypes = [C.POINTER(ScotCpbTable), vp, vp, vp, vp]
     lib.scot_cpb_bwd.restype = i
     lib.scot_attn_fwd.argtypes = [vp] * 5 + [i] * 6 + [vp]
     lib.scot_attn_fwd.restype = i
@@ -156,14 +165,74 @@ def cln_bwd(dy, zhat, rstd, time, aw, ab, dz, dz_is_f32, g_aw, g_ab, g_cw, g_cb,
                               perm_res, cur_stream()), "scot_cln_bwd")
 
 
-def cpb_fwd(w1, b1, w2, ls, tab2, alpha, ws, heads):
-    check(load().scot_cpb_fwd(ptr(w1), ptr(b1), ptr(w2), ptr(ls), ptr(tab2), ptr(alpha), ws, heads, cur_stream()),
-          "scot_cpb_fwd")
+class CpbLayerBuffers:
+    """Test helper: packs one attention layer's bias-MLP parameters / gradients / outputs into the flat
+    parameter + arena form the batched C entry points expect."""
 
+    def __init__(self, w1, b1, w2, ls, ws, heads):
+        import torch
 
-def cpb_bwd(w1, b1, w2, ls, dtab, dalpha, dpre, g_w1, g_b1, g_w2, g_ls, ws, heads):
-    check(load().scot_cpb_bwd(ptr(w1), ptr(b1), ptr(w2), ptr(ls), ptr(dtab), ptr(dalpha), ptr(dpre), ptr(g_w1), ptr(g_b1),
-                              ptr(g_w2), ptr(g_ls), ws, heads, cur_stream()), "scot_cpb_bwd")
+        dev = w1.device
+        self.ws, self.heads = ws, heads
+        R = (2 * ws - 1) ** 2
+        sizes = [w1.numel(), b1.numel(), w2.numel(), ls.numel()]
+        offs = [0]
+        for n in sizes[:-1]:
+            offs.append(offs[-1] + (n + 63) // 64 * 64)
+        self.params = torch.zeros(offs[-1] + sizes[-1] + 64, device=dev)
+        for o, t in zip(offs, (w1, b1, w2, ls)):
+            self.params[o:o + t.numel()] = t.reshape(-1).float()
+        self.grads = torch.zeros_like(self.params)
+        self.offs = offs
+        unit = lambda n: (n * 4 + 255) // 256  # noqa: E731
+        aoff, cur = [], 0
+        for n in (R * heads, heads, R * heads, heads, R * heads):
+            aoff.append(cur)
+            cur += unit(n)
+        self.arena = torch.zeros(cur * 64 + 64, device=dev)  # floats; 256 B units = 64 floats
+        shift = (-self.arena.data_ptr()) % 256 // 4
+        self.arena = self.arena[shift:]
+        self.aoff = aoff
+        self.R = R
+        t = ScotCpbTable()
+        t.n = 1
+        L_ = t.layer[0]
+        L_.w1, L_.b1, L_.w2, L_.ls = offs
+        L_.tab2, L_.alpha, L_.dtab, L_.dalpha, L_.dpre = aoff
+        L_.ws, L_.heads = ws, heads
+        self.table = t
+
+    def view(self, k, n):
+        return self.arena[self.aoff[k] * 64: self.aoff[k] * 64 + n]
+
+    @property
+    def tab2(self):
+        return self.view(0, self.R * self.heads).view(self.R, self.heads)
+
+    @property
+    def alpha(self):
+        return self.view(1, self.heads)
+
+    @property
+    def dtab(self):
+        return self.view(2, self.R * self.heads).view(self.R, self.heads)
+
+    @property
+    def dalpha(self):
+        return self.view(3, self.heads)
+
+    def grad(self, k, shape):
+        n = 1
+        for s_ in shape:
+            n *= s_
+        return self.grads[self.offs[k]: self.offs[k] + n].view(shape)
+
+    def forward(self):
+        check(load().scot_cpb_fwd(C.byref(self.table), ptr(self.params), ptr(self.arena), cur_stream()), "scot_cpb_fwd")
+
+    def backward(self):
+        check(load().scot_cpb_bwd(C.byref(self.table), ptr(self.params), ptr(self.grads), ptr(self.arena), cur_stream()),
+              "scot_cpb_bwd")
 
 
 def attn_fwd(qkv, out, lse, tab2, alpha, batch, res, ws, shift, heads, hd):

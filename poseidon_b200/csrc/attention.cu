@@ -158,61 +158,91 @@ __device__ __forceinline__ float cpb_coord(int i, int ws) {
   return s * log2f(fabsf(x) + 1.0f) / 3.0f;
 }
 
-__global__ void cpb_fwd_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                               const float* __restrict__ logit_scale, float* __restrict__ tab2, float* __restrict__ alpha,
-                               int ws, int heads) {
+// All attention layers of the model are handled by ONE launch each (blockIdx.y = layer): the per-layer work is a
+// few thousand 512-term dot products, far too small to amortise a launch of its own.
+__device__ __forceinline__ float cpb_table_value(const float* __restrict__ w1, const float* __restrict__ b1,
+                                                 const float* __restrict__ w2h, float c0, float c1, int lane) {
+  // one warp per table entry: lanes split the 512 hidden units
+  float t = 0.f;
+#pragma unroll 4
+  for (int j = lane; j < 512; j += 32) {
+    const float hid = fmaxf(fmaf(w1[2 * j], c0, fmaf(w1[2 * j + 1], c1, b1[j])), 0.f);
+    t = fmaf(w2h[j], hid, t);
+  }
+  return warp_sum(t);
+}
+
+__global__ void __launch_bounds__(256)
+cpb_fwd_kernel(ScotCpbTable tab, const float* __restrict__ params, uint8_t* __restrict__ arena) {
+  const ScotCpbLayer L = tab.layer[blockIdx.y];
+  const int ws = L.ws, heads = L.heads;
   const int side = 2 * ws - 1;
   const int total = side * side * heads;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < heads) alpha[idx] = __expf(fminf(logit_scale[idx], 4.605170185988092f));  // ln(100), HF:448
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const float* w1 = params + L.w1;
+  const float* b1 = params + L.b1;
+  const float* w2 = params + L.w2;
+  const float* ls = params + L.ls;
+  float* tab2 = reinterpret_cast<float*>(arena + (size_t)L.tab2 * 256);
+  float* alpha = reinterpret_cast<float*>(arena + (size_t)L.alpha * 256);
+  if (blockIdx.x == 0 && threadIdx.x < heads) alpha[threadIdx.x] = __expf(fminf(ls[threadIdx.x], 4.605170185988092f));  // ln 100, HF:448
   if (idx >= total) return;
   const int r = idx / heads, h = idx - r * heads;
   const float c0 = cpb_coord(r / side - (ws - 1), ws), c1 = cpb_coord(r % side - (ws - 1), ws);
-  float t = 0.f;
-  for (int j = 0; j < 512; ++j) {
-    const float hid = fmaxf(fmaf(w1[2 * j], c0, fmaf(w1[2 * j + 1], c1, b1[j])), 0.f);
-    t = fmaf(w2[h * 512 + j], hid, t);
-  }
-  tab2[idx] = 16.0f / (1.0f + __expf(-t)) * kLog2e;
+  const float t = cpb_table_value(w1, b1, w2 + h * 512, c0, c1, lane);
+  if (lane == 0) tab2[idx] = 16.0f / (1.0f + __expf(-t)) * kLog2e;
 }
 
 // dtab[r,h] = d loss / d (16*sigmoid(t)) ; produces dpre = dtab * 16 * s * (1-s) and d logit_scale
-__global__ void cpb_bwd_pre_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                                   const float* __restrict__ logit_scale, const float* __restrict__ dtab,
-                                   const float* __restrict__ dalpha, float* __restrict__ dpre,
-                                   float* __restrict__ g_logit_scale, int ws, int heads) {
+__global__ void __launch_bounds__(256)
+cpb_bwd_pre_kernel(ScotCpbTable tab, const float* __restrict__ params, float* __restrict__ grads,
+                   uint8_t* __restrict__ arena) {
+  const ScotCpbLayer L = tab.layer[blockIdx.y];
+  const int ws = L.ws, heads = L.heads;
   const int side = 2 * ws - 1;
   const int total = side * side * heads;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < heads) {
-    const float ls = logit_scale[idx];
-    // d/dls exp(min(ls, ln100)) ; torch.clamp(max=) passes gradient where ls <= max
-    if (ls <= 4.605170185988092f) atomicAdd(g_logit_scale + idx, dalpha[idx] * __expf(ls));
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const float* ls = params + L.ls;
+  const float* dtab = reinterpret_cast<const float*>(arena + (size_t)L.dtab * 256);
+  const float* dalpha = reinterpret_cast<const float*>(arena + (size_t)L.dalpha * 256);
+  float* dpre = reinterpret_cast<float*>(arena + (size_t)L.dpre * 256);
+  if (blockIdx.x == 0 && threadIdx.x < heads) {
+    const float v = ls[threadIdx.x];
+    // d/dls exp(min(ls, ln100)); torch.clamp(max=) passes the gradient where ls <= max
+    if (v <= 4.605170185988092f) atomicAdd(grads + L.ls + threadIdx.x, dalpha[threadIdx.x] * __expf(v));
   }
   if (idx >= total) return;
   const int r = idx / heads, h = idx - r * heads;
   const float c0 = cpb_coord(r / side - (ws - 1), ws), c1 = cpb_coord(r % side - (ws - 1), ws);
-  float t = 0.f;
-  for (int j = 0; j < 512; ++j) {
-    const float hid = fmaxf(fmaf(w1[2 * j], c0, fmaf(w1[2 * j + 1], c1, b1[j])), 0.f);
-    t = fmaf(w2[h * 512 + j], hid, t);
+  const float t = cpb_table_value(params + L.w1, params + L.b1, params + L.w2 + h * 512, c0, c1, lane);
+  if (lane == 0) {
+    const float sg = 1.0f / (1.0f + __expf(-t));
+    dpre[idx] = dtab[idx] * 16.0f * sg * (1.0f - sg);
   }
-  const float s = 1.0f / (1.0f + __expf(-t));
-  dpre[idx] = dtab[idx] * 16.0f * s * (1.0f - s);
 }
 
-// one thread per hidden unit j, blockIdx.y splits the table rows; register accumulation, few atomics
+// one thread per hidden unit j, blockIdx.x splits the table rows; register accumulation, few atomics
 __global__ void __launch_bounds__(512)
-cpb_bwd_mlp_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                   const float* __restrict__ dpre, float* __restrict__ g_w1, float* __restrict__ g_b1,
-                   float* __restrict__ g_w2, int ws, int heads) {
+cpb_bwd_mlp_kernel(ScotCpbTable tab, const float* __restrict__ params, float* __restrict__ grads,
+                   const uint8_t* __restrict__ arena) {
   constexpr int MAXH = 32;
+  __shared__ float sc[31 * 2];  // coordinate values per table row/column index (2*ws-1 <= 31)
+  const ScotCpbLayer L = tab.layer[blockIdx.y];
+  const int ws = L.ws, heads = L.heads;
   const int j = threadIdx.x;
   const int side = 2 * ws - 1;
   const int rows = side * side;
-  const int per = (rows + gridDim.y - 1) / gridDim.y;
-  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
-  const float wa = w1[2 * j], wb = w1[2 * j + 1], bb = b1[j];
+  if (j < side) sc[j] = cpb_coord(j - (ws - 1), ws);
+  __syncthreads();
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+  if (r0 >= r1) return;
+  const float* w1 = params + L.w1;
+  const float* w2 = params + L.w2;
+  const float* dpre = reinterpret_cast<const float*>(arena + (size_t)L.dpre * 256);
+  const float wa = w1[2 * j], wb = w1[2 * j + 1], bb = params[L.b1 + j];
   float w2j[MAXH], acc2[MAXH];
 #pragma unroll
   for (int h = 0; h < MAXH; ++h) {
@@ -221,7 +251,7 @@ cpb_bwd_mlp_kernel(const float* __restrict__ w1, const float* __restrict__ b1, c
   }
   float gwa = 0.f, gwb = 0.f, gb = 0.f;
   for (int r = r0; r < r1; ++r) {
-    const float c0 = cpb_coord(r / side - (ws - 1), ws), c1 = cpb_coord(r % side - (ws - 1), ws);
+    const float c0 = sc[r / side], c1 = sc[r % side];
     const float pre = fmaf(wa, c0, fmaf(wb, c1, bb));
     const float hid = fmaxf(pre, 0.f);
     float dh = 0.f;
@@ -241,10 +271,10 @@ cpb_bwd_mlp_kernel(const float* __restrict__ w1, const float* __restrict__ b1, c
   }
 #pragma unroll
   for (int h = 0; h < MAXH; ++h)
-    if (h < heads) atomicAdd(g_w2 + h * 512 + j, acc2[h]);
-  atomicAdd(g_w1 + 2 * j, gwa);
-  atomicAdd(g_w1 + 2 * j + 1, gwb);
-  atomicAdd(g_b1 + j, gb);
+    if (h < heads) atomicAdd(grads + L.w2 + h * 512 + j, acc2[h]);
+  atomicAdd(grads + L.w1 + 2 * j, gwa);
+  atomicAdd(grads + L.w1 + 2 * j + 1, gwb);
+  atomicAdd(grads + L.b1 + j, gb);
 }
 
 // =================================================================================================
@@ -622,8 +652,15 @@ attn_bias_reduce_kernel(const float* __restrict__ partial, float* __restrict__ d
   const int per_cta = (PER_HEAD + gridDim.y - 1) / gridDim.y;
   const int p0 = blockIdx.y * per_cta, p1 = min(PER_HEAD, p0 + per_cta);
   for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
-    float v = 0.f;
-    for (int c = 0; c < chunks; ++c) v += partial[((long)c * heads + h) * PER_HEAD + p];
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    const float* src = partial + (long)h * PER_HEAD + p;
+    const long cs = (long)heads * PER_HEAD;
+    int c = 0;
+    for (; c + 4 <= chunks; c += 4) {
+      v0 += src[(c + 0) * cs]; v1 += src[(c + 1) * cs]; v2 += src[(c + 2) * cs]; v3 += src[(c + 3) * cs];
+    }
+    for (; c < chunks; ++c) v0 += src[c * cs];
+    const float v = (v0 + v1) + (v2 + v3);
     // decode slot -> (row m, col n)
     const int rgw = p / (16 * N);      // rg * NWARP + warp
     const int slot = p - rgw * 16 * N;
@@ -887,24 +924,31 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
     SCOT_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::smem));
     done = true;
   }
-  // chunks of windows so that the grid covers the machine about twice
+  // dq kernel: ~200 KB of smem -> one CTA per SM, so size the grid to a single wave; fewer chunks also means
+  // fewer bias-gradient dumps for the second-stage reduction
   const int iters = ceil_div(total_windows, C1::WPI);
-  int chunks = ceil_div(2 * num_sms(), g.heads * C1::RG);
+  int chunks = num_sms() / (g.heads * C1::RG);
   if (chunks > iters) chunks = iters;
   if (chunks < 1) chunks = 1;
   int wpc = ceil_div(iters, chunks) * C1::WPI;
   chunks = ceil_div(total_windows, wpc);
   const size_t need = (size_t)chunks * g.heads * C1::RG * NWARP * C1::ACC_PER_WARP * sizeof(float);
   SCOT_REQUIRE(need <= partial_bytes, "attention backward: bias partial buffer too small (%zu > %zu)", need, partial_bytes);
+  // dk/dv kernel: ~66 KB of smem -> three CTAs per SM
+  int chunks2 = (3 * num_sms()) / (g.heads * C2::KG);
+  if (chunks2 > iters) chunks2 = iters;
+  if (chunks2 < 1) chunks2 = 1;
+  const int wpc2 = ceil_div(iters, chunks2) * C2::WPI;
+  chunks2 = ceil_div(total_windows, wpc2);
   dim3 grid1(g.heads, C1::RG, chunks);
   k1<<<grid1, NWARP * 32, C1::smem, st>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, tab2, alpha, (bf16*)dqkv,
                                            partial, dalpha, g_qbias, g, total_windows, wpc);
   SCOT_LAUNCH_CHECK();
-  dim3 grid2(g.heads, C2::KG, chunks);
+  dim3 grid2(g.heads, C2::KG, chunks2);
   k2<<<grid2, NWARP * 32, C2::smem, st>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, tab2, alpha, (bf16*)dqkv,
-                                           g_vbias, g, total_windows, wpc);
+                                           g_vbias, g, total_windows, wpc2);
   SCOT_LAUNCH_CHECK();
-  const int red_y = WS == 16 ? 16 : (WS == 8 ? 2 : 1);
+  const int red_y = WS == 16 ? 64 : (WS == 8 ? 4 : 1);
   attn_bias_reduce_kernel<WS, NWARP><<<dim3(g.heads, red_y), 256, 0, st>>>(partial, dtab, g.heads, chunks);
   SCOT_LAUNCH_CHECK();
   return 0;
@@ -923,25 +967,30 @@ size_t scot_attn_bwd_partial_bytes(int ws, int heads, int total_windows) {
   return (size_t)chunks * heads * rg * nwarp * 16 * N * sizeof(float);
 }
 
-int scot_cpb_fwd_launch(const float* w1, const float* b1, const float* w2, const float* logit_scale, float* tab2,
-                        float* alpha, int ws, int heads, cudaStream_t st) {
-  SCOT_REQUIRE(w1 && b1 && w2 && logit_scale && tab2 && alpha, "cpb_fwd: null pointer");
-  const int total = (2 * ws - 1) * (2 * ws - 1) * heads;
-  cpb_fwd_kernel<<<ceil_div(total > heads ? total : heads, 128), 128, 0, st>>>(w1, b1, w2, logit_scale, tab2, alpha, ws, heads);
+int scot_cpb_fwd_launch(const ScotCpbTable* tab, const float* params, void* arena, cudaStream_t st) {
+  SCOT_REQUIRE(tab && params && arena && tab->n >= 1 && tab->n <= SCOT_CPB_MAX_LAYERS, "cpb_fwd: bad table");
+  int max_total = 0;
+  for (int i = 0; i < tab->n; ++i) {
+    const int t = (2 * tab->layer[i].ws - 1) * (2 * tab->layer[i].ws - 1) * tab->layer[i].heads;
+    max_total = t > max_total ? t : max_total;
+    SCOT_REQUIRE(tab->layer[i].heads <= 32 && tab->layer[i].ws <= 16, "cpb: at most 32 heads / window 16");
+  }
+  cpb_fwd_kernel<<<dim3(ceil_div(max_total, 8), tab->n), 256, 0, st>>>(*tab, params, (uint8_t*)arena);
   SCOT_LAUNCH_CHECK();
   return 0;
 }
 
-int scot_cpb_bwd_launch(const float* w1, const float* b1, const float* w2, const float* logit_scale, const float* dtab,
-                        const float* dalpha, float* dpre_ws, float* g_w1, float* g_b1, float* g_w2, float* g_ls, int ws,
-                        int heads, cudaStream_t st) {
-  SCOT_REQUIRE(heads <= 32, "cpb_bwd: at most 32 heads supported");
-  const int total = (2 * ws - 1) * (2 * ws - 1) * heads;
-  cpb_bwd_pre_kernel<<<ceil_div(total, 128), 128, 0, st>>>(w1, b1, w2, logit_scale, dtab, dalpha, dpre_ws, g_ls, ws, heads);
+int scot_cpb_bwd_launch(const ScotCpbTable* tab, const float* params, float* grads, void* arena, cudaStream_t st) {
+  SCOT_REQUIRE(tab && params && grads && arena && tab->n >= 1 && tab->n <= SCOT_CPB_MAX_LAYERS, "cpb_bwd: bad table");
+  int max_total = 0;
+  for (int i = 0; i < tab->n; ++i) {
+    const int t = (2 * tab->layer[i].ws - 1) * (2 * tab->layer[i].ws - 1) * tab->layer[i].heads;
+    max_total = t > max_total ? t : max_total;
+    SCOT_REQUIRE(tab->layer[i].heads <= 32 && tab->layer[i].ws <= 16, "cpb: at most 32 heads / window 16");
+  }
+  cpb_bwd_pre_kernel<<<dim3(ceil_div(max_total, 8), tab->n), 256, 0, st>>>(*tab, params, grads, (uint8_t*)arena);
   SCOT_LAUNCH_CHECK();
-  const int rows = (2 * ws - 1) * (2 * ws - 1);
-  const int gy = rows >= 512 ? 16 : (rows >= 128 ? 4 : 1);
-  cpb_bwd_mlp_kernel<<<dim3(1, gy), 512, 0, st>>>(w1, b1, w2, dpre_ws, g_w1, g_b1, g_w2, ws, heads);
+  cpb_bwd_mlp_kernel<<<dim3(16, tab->n), 512, 0, st>>>(*tab, params, grads, (const uint8_t*)arena);
   SCOT_LAUNCH_CHECK();
   return 0;
 }

@@ -41,15 +41,11 @@ int scot_cln_bwd(const float* dy, const void* zhat, const float* rstd, const flo
   return scot_cln_bwd_launch(dy, zhat, rstd, time, aw, ab, dz, dz_is_f32, g_aw, g_ab, g_cw, g_cb, g_bias_prev, rows, C,
                              rows_per_sample, perm_res, (cudaStream_t)stream);
 }
-int scot_cpb_fwd(const float* w1, const float* b1, const float* w2, const float* logit_scale, float* tab2, float* alpha,
-                 int ws, int heads, void* stream) {
-  return scot_cpb_fwd_launch(w1, b1, w2, logit_scale, tab2, alpha, ws, heads, (cudaStream_t)stream);
+int scot_cpb_fwd(const ScotCpbTable* table, const float* params, void* arena, void* stream) {
+  return scot_cpb_fwd_launch(table, params, arena, (cudaStream_t)stream);
 }
-int scot_cpb_bwd(const float* w1, const float* b1, const float* w2, const float* logit_scale, const float* dtab,
-                 const float* dalpha, float* dpre_ws, float* g_w1, float* g_b1, float* g_w2, float* g_ls, int ws, int heads,
-                 void* stream) {
-  return scot_cpb_bwd_launch(w1, b1, w2, logit_scale, dtab, dalpha, dpre_ws, g_w1, g_b1, g_w2, g_ls, ws, heads,
-                             (cudaStream_t)stream);
+int scot_cpb_bwd(const ScotCpbTable* table, const float* params, float* grads, void* arena, void* stream) {
+  return scot_cpb_bwd_launch(table, params, grads, arena, (cudaStream_t)stream);
 }
 int scot_attn_fwd(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, int batch, int res, int ws,
                   int shift, int heads, int head_dim, void* stream) {

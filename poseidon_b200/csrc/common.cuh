@@ -59,13 +59,31 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// erf-GELU (nn.GELU default, reference ACT2FN["gelu"]) with the Abramowitz-Stegun 7.1.26 rational/exponential form of
+// erf (|abs err| <= 1.5e-7, far below the bf16 the result is stored in): one ex2, one rcp and a handful of FMAs
+// instead of erff's ~40-instruction path — the GEMM epilogues run on only four warps per CTA.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;           // |x|/sqrt(2)
+  const float e2 = __expf(-0.5f * x * x);                         // exp(-x^2/2) = exp(-ax^2)
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfc_ax = poly * t * e2;                            // 1 - erf(|x|/sqrt 2)
+  const float half_erfc = 0.5f * erfc_ax;
+  cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;                  // Phi(x)
+  pdf = 0.39894228040143267794f * e2;                             // phi(x)
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float cdf, pdf;
+  gelu_parts(x, cdf, pdf);
+  return x * cdf;
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, pdf;
+  gelu_parts(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);

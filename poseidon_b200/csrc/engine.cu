@@ -6,6 +6,7 @@
 // workspace arena) belongs to the caller; the engine object only holds host-side plans (offsets), so one
 // forward+backward is a fixed sequence of kernel launches on the caller's stream and can be captured in
 // a CUDA graph.
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,7 +43,7 @@ struct Geo {
 
 // offsets (bytes) into the caller's arena
 struct BlockBuf {
-  size_t qkv, o, lse, zhat1, rstd1, y1b, h, g, zhat2, rstd2, xout, xbout, tab2, alpha, dtab, dalpha;
+  size_t qkv, o, lse, zhat1, rstd1, y1b, h, g, zhat2, rstd2, xout, xbout, tab2, alpha, dtab, dalpha, dpre;
 };
 struct NormBuf { size_t zhat, rstd; };
 struct CnxBuf { size_t nb, h, g, z2b, out, zhat, rstd; };
@@ -84,12 +85,13 @@ struct ScotEngine {
   std::vector<size_t> u_nb, u_x, u_xb;   // unmerge: normalised (bf16), decoder stage input fp32 / bf16
   std::vector<std::vector<CnxBuf>> cbuf;
   std::vector<size_t> skip_xb;           // bf16 copy of the post-ConvNeXt skip of the last stage (if any)
-  size_t rec_bias, rec_D, pred_copy, loss_sums;
+  size_t rec_bias, rec_D, rec_P, pred_copy, loss_sums;
   size_t z32, y32;                       // fp32 scratch [M0*C0] each
   // backward scratch
   size_t dzb, dqkv, dh, dob, partial, dpre, dpred, dD16, dgrads_zero_begin, dgrads_zero_bytes;
   size_t partial_bytes;
   std::vector<size_t> gstage;            // fp32 [M_s, C_s]
+  std::vector<ScotCpbTable> cpb_tables;  // relative-position-bias MLPs of all attention layers (<= 64 per table)
   // forward state needed by backward
   const float* last_pixels = nullptr;
   const float* last_time = nullptr;
@@ -319,6 +321,7 @@ int build_plan(ScotEngine* e) {
   }
   e->rec_bias = b.take(NR * 4);
   e->rec_D = b.take(M0 * NR * 4);
+  e->rec_P = b.take(M0 * NR * 4);
   e->loss_sums = b.take(64 * 4);
   e->z32 = b.take(M0 * C0 * 4);
   e->y32 = b.take(M0 * C0 * 4);
@@ -342,7 +345,7 @@ int build_plan(ScotEngine* e) {
   }
   e->partial_bytes = pb;
   e->partial = b.take(pb);
-  e->dpre = b.take((size_t)31 * 31 * 32 * 4);
+  e->dpre = 0;
   e->dpred = b.take((size_t)e->batch * d.num_out_channels * d.image_size * d.image_size * 4);
   e->dD16 = b.take(M0 * NR * 2);
   // per-layer bias-table gradient accumulators (zeroed at the start of every backward)
@@ -351,11 +354,39 @@ int build_plan(ScotEngine* e) {
     bb.dtab = b.take((size_t)(2 * g.ws - 1) * (2 * g.ws - 1) * g.heads * 4);
     bb.dalpha = b.take((size_t)g.heads * 4);
   };
+  auto plan_dpre = [&](BlockBuf& bb, const Geo& g) { bb.dpre = b.take((size_t)(2 * g.ws - 1) * (2 * g.ws - 1) * g.heads * 4); };
   for (int s = 0; s < e->ns; ++s)
     for (auto& bb : e->ebuf[s]) plan_dt(bb, e->geo[s]);
   for (int j = 0; j < e->ns; ++j)
     for (auto& bb : e->dbuf[j]) plan_dt(bb, e->geo[e->ns - 1 - j]);
   e->dgrads_zero_bytes = b.off - e->dgrads_zero_begin;
+  for (int s = 0; s < e->ns; ++s)
+    for (auto& bb : e->ebuf[s]) plan_dpre(bb, e->geo[s]);
+  for (int j = 0; j < e->ns; ++j)
+    for (auto& bb : e->dbuf[j]) plan_dpre(bb, e->geo[e->ns - 1 - j]);
+  // descriptor tables for the batched bias-MLP kernels
+  {
+    std::vector<ScotCpbLayer> all;
+    auto add_layer = [&](const BlockP& p, const BlockBuf& bb, const Geo& g) {
+      ScotCpbLayer L;
+      L.w1 = (int)p.cw1; L.b1 = (int)p.cb1; L.w2 = (int)p.cw2; L.ls = (int)p.ls;
+      L.tab2 = (int)(bb.tab2 / 256); L.alpha = (int)(bb.alpha / 256);
+      L.dtab = (int)(bb.dtab / 256); L.dalpha = (int)(bb.dalpha / 256); L.dpre = (int)(bb.dpre / 256);
+      L.ws = (short)g.ws; L.heads = (short)g.heads;
+      all.push_back(L);
+    };
+    for (int s = 0; s < e->ns; ++s)
+      for (int i = 0; i < e->geo[s].depth; ++i) add_layer(e->enc[s][i], e->ebuf[s][i], e->geo[s]);
+    for (int j = 0; j < e->ns; ++j)
+      for (int i = 0; i < e->geo[e->ns - 1 - j].depth; ++i) add_layer(e->dec[j][i], e->dbuf[j][i], e->geo[e->ns - 1 - j]);
+    for (size_t i = 0; i < all.size(); i += SCOT_CPB_MAX_LAYERS) {
+      ScotCpbTable t;
+      memset(&t, 0, sizeof(t));
+      t.n = (int)std::min<size_t>(SCOT_CPB_MAX_LAYERS, all.size() - i);
+      for (int k = 0; k < t.n; ++k) t.layer[k] = all[i + k];
+      e->cpb_tables.push_back(t);
+    }
+  }
   e->gstage.resize(e->ns);
   for (int s = 0; s < e->ns; ++s) e->gstage[s] = b.take((size_t)e->geo[s].M * e->geo[s].C * 4);
   e->ws_bytes = b.off;
@@ -452,8 +483,6 @@ int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, in
                           g.hd, c.st));
   RC(gemm(c, dqkv, 3 * C, 1, xb_in, C, 1, 3 * C, C, M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.wqkv), C));
   RC(gemm(c, dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
-  RC(scot_cpb_bwd_launch(c.p(p.cw1), c.p(p.cb1), c.p(p.cw2), c.p(p.ls), c.at<float>(b.dtab), c.at<float>(b.dalpha),
-                         c.at<float>(e->dpre), c.g(p.cw1), c.g(p.cb1), c.g(p.cw2), c.g(p.ls), g.ws, g.heads, c.st));
   return 0;
 }
 
@@ -543,19 +572,8 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
   const Geo& g0 = e->geo[0];
   // bf16 copy of all parameters (GEMM operands)
   RC(scot_cast_f32_bf16_launch(params, c.at<bf16>(e->wb16), e->n_elems, c.st));
-  // relative-position-bias tables for every attention layer (batch independent)
-  for (int s = 0; s < ns; ++s) {
-    for (int i = 0; i < e->geo[s].depth; ++i) {
-      const BlockP& p = e->enc[s][i];
-      const BlockBuf& b = e->ebuf[s][i];
-      RC(scot_cpb_fwd_launch(c.p(p.cw1), c.p(p.cb1), c.p(p.cw2), c.p(p.ls), c.at<float>(b.tab2), c.at<float>(b.alpha),
-                             e->geo[s].ws, e->geo[s].heads, c.st));
-      const BlockP& q = e->dec[ns - 1 - s][i];
-      const BlockBuf& bq = e->dbuf[ns - 1 - s][i];
-      RC(scot_cpb_fwd_launch(c.p(q.cw1), c.p(q.cb1), c.p(q.cw2), c.p(q.ls), c.at<float>(bq.tab2), c.at<float>(bq.alpha),
-                             e->geo[s].ws, e->geo[s].heads, c.st));
-    }
-  }
+  // relative-position-bias tables of every attention layer (batch independent), one launch
+  for (const ScotCpbTable& t : e->cpb_tables) RC(scot_cpb_fwd_launch(&t, params, arena, c.st));
   // ---- embeddings (scOT/model.py:295-310, 345-366) ----
   const int K0 = d.num_channels * d.patch_size * d.patch_size;
   RC(scot_im2col_patch_launch(pixel_values, c.at<bf16>(e->p16), B, d.num_channels, d.image_size, d.image_size, d.patch_size,
@@ -643,9 +661,10 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
   RC(gemm(c, xb, g0.C, 0, c.w16(e->rec_w), NR, 1, g0.M, NR, g0.C, SCOT_EPI_F32, c.at<float>(e->rec_bias),
           c.at<float>(e->rec_D), NR));
   const float* resid = d.learn_residual ? pixel_values : nullptr;
-  RC(scot_conv5_fwd_launch(c.at<float>(e->rec_D), c.p(e->rec_mix), resid, d.num_channels, labels, mask,
-                           labels ? mask_mode : 0, pred_out, B, d.num_out_channels, d.image_size, d.image_size,
+  RC(scot_unshuffle_launch(c.at<float>(e->rec_D), c.at<float>(e->rec_P), B, d.num_out_channels, d.image_size, d.image_size,
                            d.patch_size, c.st));
+  RC(scot_conv5_fwd_launch(c.at<float>(e->rec_P), c.p(e->rec_mix), resid, d.num_channels, labels, mask,
+                           labels ? mask_mode : 0, pred_out, B, d.num_out_channels, d.image_size, d.image_size, c.st));
   if (labels != nullptr) {
     RC(scot_loss_fwd_launch(pred_out, labels, c.at<float>(e->loss_sums), loss_out, d.n_slices >= 2 ? d.slices : nullptr,
                             d.n_slices, d.loss_p, B, d.num_out_channels, (long)d.image_size * d.image_size, c.st));
@@ -678,8 +697,10 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
   RC(scot_loss_bwd_launch(e->last_pred, e->last_labels, c.at<float>(e->loss_sums), grad_loss, grad_pred, e->last_mask,
                           e->last_mask_mode, dpred, d.n_slices >= 2 ? d.slices : nullptr, d.n_slices, d.loss_p, B,
                           d.num_out_channels, HW, c.st));
-  RC(scot_conv5_bwd_launch(c.at<float>(e->rec_D), c.p(e->rec_mix), dpred, c.at<bf16>(e->dD16), c.g(e->rec_mix),
-                           c.g(e->rec_b), B, d.num_out_channels, d.image_size, d.image_size, d.patch_size, c.st));
+  // rec_D (token-major deconv output) is dead after the forward un-shuffle: reuse it as the planar dP scratch
+  RC(scot_conv5_bwd_launch(c.at<float>(e->rec_P), c.p(e->rec_mix), dpred, c.at<float>(e->rec_D), c.at<bf16>(e->dD16),
+                           c.g(e->rec_mix), c.g(e->rec_b), B, d.num_out_channels, d.image_size, d.image_size, d.patch_size,
+                           c.st));
   // final decoder output (bf16) = input of the recovery GEMM
   const BlockBuf& lastb = e->dbuf[ns - 1].back();
   const bf16* xb_final = c.at<bf16>(lastb.xbout);
@@ -776,6 +797,8 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
                 c.g(e->emb_b), g0.M, g0.C, g0.res * g0.res, 0));
     RC(gemm(c, dzb, g0.C, 1, c.at<bf16>(e->p16), K0, 1, g0.C, K0, g0.M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(e->emb_w), K0));
   }
+  // ---- relative-position-bias MLPs + logit scales of all attention layers (batched) ----
+  for (const ScotCpbTable& t : e->cpb_tables) RC(scot_cpb_bwd_launch(&t, params, grads, arena, c.st));
   return 0;
 }
 

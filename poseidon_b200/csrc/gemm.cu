@@ -38,12 +38,25 @@ struct EpiArgs {
 };
 
 // ---- fused epilogue on a float4 of accumulators at (row, col..col+3); col is a multiple of 4 ----------
+// auxiliary global operand of the epilogue (loaded ahead of the math so that several rows are in flight)
 template <int MODE>
-__device__ __forceinline__ void epi_store(const EpiArgs& ep, long row, int col, float4 v, float4& csum) {
-  if (ep.bias != nullptr) {
-    const float4 b = *reinterpret_cast<const float4*>(ep.bias + col);
-    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+__device__ __forceinline__ float4 epi_load_aux(const EpiArgs& ep, long row, int col) {
+  if constexpr (MODE == SCOT_EPI_GELU_BWD) {
+    const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + row * ep.ldaux + col);
+    return make_float4(__uint_as_float(h.x), __uint_as_float(h.y), 0.f, 0.f);
+  } else if constexpr (MODE == SCOT_EPI_RMW_F32) {
+    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.out0) + row * ep.ld0 + col);
+  } else if constexpr (MODE == SCOT_EPI_ADD_F32_BF16) {
+    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.aux) + row * ep.ldaux + col);
+  } else {
+    return make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_store(const EpiArgs& ep, long row, int col, float4 v, float4 aux, float4 bias,
+                                          float4& csum) {
+  v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
   if constexpr (MODE == SCOT_EPI_BF16) {
     uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + row * ep.ld0 + col) = o;
@@ -59,8 +72,7 @@ __device__ __forceinline__ void epi_store(const EpiArgs& ep, long row, int col, 
       *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + row * ep.ld0 + col) = o0;
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out1) + row * ep.ld1 + col) = o1;
   } else if constexpr (MODE == SCOT_EPI_GELU_BWD) {
-    const uint2 hraw = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + row * ep.ldaux + col);
-    const float2 h01 = unpack_bf16x2(hraw.x), h23 = unpack_bf16x2(hraw.y);
+    const float2 h01 = unpack_bf16x2(__float_as_uint(aux.x)), h23 = unpack_bf16x2(__float_as_uint(aux.y));
     v.x *= gelu_erf_grad(h01.x); v.y *= gelu_erf_grad(h01.y);
     v.z *= gelu_erf_grad(h23.x); v.w *= gelu_erf_grad(h23.y);
     uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
@@ -69,17 +81,14 @@ __device__ __forceinline__ void epi_store(const EpiArgs& ep, long row, int col, 
     csum.x += r01.x; csum.y += r01.y; csum.z += r23.x; csum.w += r23.y;
   } else if constexpr (MODE == SCOT_EPI_RMW_F32) {
     float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + row * ep.ld0 + col);
-    float4 o = *p;
-    o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
-    *p = o;
+    *p = make_float4(aux.x + v.x, aux.y + v.y, aux.z + v.z, aux.w + v.w);
   } else if constexpr (MODE == SCOT_EPI_ATOMIC_F32) {
     float* p = reinterpret_cast<float*>(ep.out0) + row * ep.ld0 + col;
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
   } else if constexpr (MODE == SCOT_EPI_ADD_F32_BF16) {
     // out0 (fp32) = acc + aux (fp32 residual); out1 (bf16 copy) = same value rounded
-    const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.aux) + row * ep.ldaux + col);
-    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    v.x += aux.x; v.y += aux.y; v.z += aux.z; v.w += aux.w;
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + row * ep.ld0 + col) = v;
     if (ep.out1 != nullptr) {
       uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
@@ -217,11 +226,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int col = n0 + cv * 4;
       float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r0 < RPP && col < N) {
-        for (int r = r0; r < BM; r += RPP) {
-          const long row = (long)m0 + r;
-          if (row >= M) break;
-          const float4 v = *reinterpret_cast<const float4*>(stage + (size_t)r * Cfg::kStagePitch + cv * 4);
-          epi_store<MODE>(ep, row, col, v, csum);
+        const float4 bias = ep.bias != nullptr ? *reinterpret_cast<const float4*>(ep.bias + col)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int U = 4;  // rows in flight per thread (independent global loads issued back to back)
+        for (int r = r0; r < BM; r += RPP * U) {
+          float4 v[U], aux[U];
+          bool ok[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int ru = r + u * RPP;
+            ok[u] = ru < BM && (long)m0 + ru < M;
+            if (ok[u]) {
+              aux[u] = epi_load_aux<MODE>(ep, (long)m0 + ru, col);
+              v[u] = *reinterpret_cast<const float4*>(stage + (size_t)ru * Cfg::kStagePitch + cv * 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (ok[u]) epi_store<MODE>(ep, (long)m0 + r + u * RPP, col, v[u], aux[u], bias, csum);
         }
         if constexpr (MODE == SCOT_EPI_GELU_BWD) {
           if (ep.colsum != nullptr) {
@@ -261,7 +283,8 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, long lda, int amn, 
     }
   }
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-  epi_store<MODE>(ep, row, col, make_float4(acc[0], acc[1], acc[2], acc[3]), csum);
+  const float4 bias = ep.bias != nullptr ? *reinterpret_cast<const float4*>(ep.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+  epi_store<MODE>(ep, row, col, make_float4(acc[0], acc[1], acc[2], acc[3]), epi_load_aux<MODE>(ep, row, col), bias, csum);
   if constexpr (MODE == SCOT_EPI_GELU_BWD) {
     if (ep.colsum != nullptr) {
       atomicAdd(ep.colsum + col + 0, csum.x);
@@ -335,7 +358,7 @@ int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, in
   splits = ceil_div(kblocks, kps);  // no empty split
 
   int min_stages = ceil_div(Cfg::kStagingBytes, Cfg::kStageBytes);
-  int stages = kps < 4 ? kps : 4;
+  int stages = kps < 3 ? kps : 3;  // 3 stages keep two CTAs resident per SM (epilogue of one overlaps loads of the other)
   if (stages < min_stages) stages = min_stages;
   if (stages < 2) stages = 2;
   SCOT_REQUIRE(stages <= 8, "gemm: too many stages");

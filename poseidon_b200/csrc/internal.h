@@ -15,11 +15,8 @@ int scot_cln_bwd_launch(const float* dy, const void* zhat, const float* rstd, co
                         float* g_bias_prev, long rows, int C, int rows_per_sample, int perm_res, cudaStream_t st);
 // attention.cu
 size_t scot_attn_bwd_partial_bytes(int ws, int heads, int total_windows);
-int scot_cpb_fwd_launch(const float* w1, const float* b1, const float* w2, const float* logit_scale, float* tab2,
-                        float* alpha, int ws, int heads, cudaStream_t st);
-int scot_cpb_bwd_launch(const float* w1, const float* b1, const float* w2, const float* logit_scale, const float* dtab,
-                        const float* dalpha, float* dpre_ws, float* g_w1, float* g_b1, float* g_w2, float* g_ls, int ws,
-                        int heads, cudaStream_t st);
+int scot_cpb_fwd_launch(const ScotCpbTable* tab, const float* params, void* arena, cudaStream_t st);
+int scot_cpb_bwd_launch(const ScotCpbTable* tab, const float* params, float* grads, void* arena, cudaStream_t st);
 int scot_attn_fwd_launch(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, int batch,
                          int res, int ws, int shift, int heads, int hd, cudaStream_t st);
 int scot_attn_bwd_launch(const void* qkv, const void* o, const void* d_o, const float* lse, const float* tab2,
@@ -40,11 +37,11 @@ int scot_dwconv7_fwd_launch(const float* x, const float* w, const float* bias, f
                             cudaStream_t st);
 int scot_dwconv7_bwd_launch(const float* x, const float* w, const float* dout, const float* g_in, float* g_out, float* g_w,
                             int B, int res, int C, cudaStream_t st);
-int scot_conv5_fwd_launch(const float* D, const float* w, const float* resid, int resid_channels, const float* labels,
-                          const uint8_t* mask, int mask_mode, float* pred, int B, int OC, int H, int W, int ps,
-                          cudaStream_t st);
-int scot_conv5_bwd_launch(const float* D, const float* w, const float* dpred, void* dD, float* g_w, float* g_bias, int B,
-                          int OC, int H, int W, int ps, cudaStream_t st);
+int scot_unshuffle_launch(const float* D, float* P, int B, int OC, int H, int W, int ps, cudaStream_t st);
+int scot_conv5_fwd_launch(const float* P, const float* w, const float* resid, int resid_channels, const float* labels,
+                          const uint8_t* mask, int mask_mode, float* pred, int B, int OC, int H, int W, cudaStream_t st);
+int scot_conv5_bwd_launch(const float* P, const float* w, const float* dpred, float* dP_scratch, void* dD, float* g_w,
+                          float* g_bias, int B, int OC, int H, int W, int ps, cudaStream_t st);
 int scot_loss_fwd_launch(const float* pred, const float* labels, float* sums, float* loss, const int* slices_host,
                          int n_slices, int p, int B, int OC, long HW, cudaStream_t st);
 int scot_loss_bwd_launch(const float* pred, const float* labels, const float* sums, const float* gscale, const float* extra,

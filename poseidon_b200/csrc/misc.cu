@@ -135,85 +135,131 @@ scale_add_bwd_kernel(const float* __restrict__ g, const bf16* __restrict__ zb, c
 }
 
 // ---- depthwise 7x7 (NHWC fp32, zero padding 3) -------------------------------------------------------
+// One thread = 8 consecutive x positions x 4 channels: per filter row it loads 14 input float4 and 28 weights for
+// 224 FMAs (register sliding window) instead of one load per FMA.
 // FLIP=false: out = conv(x, w) + bias ; FLIP=true (data gradient): out = add + conv(x, flipped w)
 template <bool FLIP>
-__global__ void dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                               const float* __restrict__ add, float* __restrict__ out, int B, int res, int C) {
-  const int c4n = C / 4;
-  const long total = (long)B * res * res * c4n;
+__global__ void __launch_bounds__(128)
+dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+               const float* __restrict__ add, float* __restrict__ out, int B, int res, int C) {
+  const int c4n = C / 4, xg = (res + 7) / 8;
+  const long total = (long)B * res * xg * c4n;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c4 = (int)(i % c4n);
   long t = i / c4n;
-  const int px = (int)(t % res);
-  t /= res;
+  const int gx = (int)(t % xg);
+  t /= xg;
   const int py = (int)(t % res);
   const int b = (int)(t / res);
-  const int c = c4 * 4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (bias != nullptr) acc = *reinterpret_cast<const float4*>(bias + c);
+  const int c = c4 * 4, x0 = gx * 8;
+  float4 acc[8];
+  const float4 bz = bias != nullptr ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = bz;
+#pragma unroll 1
   for (int ky = 0; ky < 7; ++ky) {
     const int yy = py + ky - 3;
     if (yy < 0 || yy >= res) continue;
+    float4 in[14];
+    const float* rowp = x + (((long)b * res + yy) * res) * C + c;
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      const int xx = x0 + k - 3;
+      in[k] = (xx >= 0 && xx < res) ? *reinterpret_cast<const float4*>(rowp + (long)xx * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
     for (int kx = 0; kx < 7; ++kx) {
-      const int xx = px + kx - 3;
-      if (xx < 0 || xx >= res) continue;
-      const float4 v = *reinterpret_cast<const float4*>(x + (((long)b * res + yy) * res + xx) * C + c);
       const int tap = FLIP ? (6 - ky) * 7 + (6 - kx) : ky * 7 + kx;
-      acc.x = fmaf(v.x, w[(c + 0) * 49 + tap], acc.x);
-      acc.y = fmaf(v.y, w[(c + 1) * 49 + tap], acc.y);
-      acc.z = fmaf(v.z, w[(c + 2) * 49 + tap], acc.z);
-      acc.w = fmaf(v.w, w[(c + 3) * 49 + tap], acc.w);
+      const float w0 = w[(c + 0) * 49 + tap], w1 = w[(c + 1) * 49 + tap], w2 = w[(c + 2) * 49 + tap], w3 = w[(c + 3) * 49 + tap];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[k].x = fmaf(in[k + kx].x, w0, acc[k].x);
+        acc[k].y = fmaf(in[k + kx].y, w1, acc[k].y);
+        acc[k].z = fmaf(in[k + kx].z, w2, acc[k].z);
+        acc[k].w = fmaf(in[k + kx].w, w3, acc[k].w);
+      }
     }
   }
-  const long o = (((long)b * res + py) * res + px) * C + c;
-  if (add != nullptr) {
-    const float4 a = *reinterpret_cast<const float4*>(add + o);
-    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int xx = x0 + k;
+    if (xx >= res) break;
+    const long o = (((long)b * res + py) * res + xx) * C + c;
+    float4 v = acc[k];
+    if (add != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(add + o);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    *reinterpret_cast<float4*>(out + o) = v;
   }
-  *reinterpret_cast<float4*>(out + o) = acc;
 }
 // weight gradient: g_w[c,ky,kx] += sum_{b,y,x} dout[b,y,x,c] * x[b,y+ky-3,x+kx-3,c]
-// block: 64 "tap" threads (49 used) x 4 channel quads; grid = (C/16, pixel chunks)
+// block = (filter row ky, group of images); thread = (channel quad, row lane) sweeps image rows with a 7-wide
+// register window, accumulating its 7x4 taps; block-level smem reduction, then one atomic per tap per block.
 __global__ void __launch_bounds__(256)
 dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dout, float* __restrict__ g_w, int B, int res,
-                     int C, int pix_per_block) {
-  const int tap = threadIdx.x & 63, quad = threadIdx.x >> 6;
-  const int c = (blockIdx.x * 4 + quad) * 4;
-  if (tap >= 49 || c >= C) return;
-  const int ky = tap / 7, kx = tap - ky * 7;
-  const long npix = (long)B * res * res;
-  const long p0 = (long)blockIdx.y * pix_per_block;
-  const long p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long p = p0; p < p1; ++p) {
-    const int px = (int)(p % res);
-    const long t = p / res;
-    const int py = (int)(t % res);
-    const int yy = py + ky - 3, xx = px + kx - 3;
-    if (yy < 0 || yy >= res || xx < 0 || xx >= res) continue;
-    const float4 d = *reinterpret_cast<const float4*>(dout + p * C + c);
-    const float4 v = *reinterpret_cast<const float4*>(x + (p + (long)(ky - 3) * res + (kx - 3)) * C + c);
-    acc.x = fmaf(d.x, v.x, acc.x); acc.y = fmaf(d.y, v.y, acc.y);
-    acc.z = fmaf(d.z, v.z, acc.z); acc.w = fmaf(d.w, v.w, acc.w);
+                     int C, int imgs_per_block) {
+  extern __shared__ float sred[];  // [28][C/4] accumulated with smem atomics
+  const int c4n = C / 4;
+  const int ky = blockIdx.x;
+  const int b0 = blockIdx.y * imgs_per_block;
+  const int lanes = blockDim.x / c4n;            // row lanes
+  const int c4 = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+  for (int k = threadIdx.x; k < 28 * c4n; k += blockDim.x) sred[k] = 0.f;
+  __syncthreads();
+  if (rl < lanes) {
+    const int c = c4 * 4;
+    float4 acc[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nrows = imgs_per_block * res;
+    for (int r = rl; r < nrows; r += lanes) {
+      const int b = b0 + r / res, y = r % res;
+      if (b >= B) break;
+      const int yy = y + ky - 3;
+      if (yy < 0 || yy >= res) continue;
+      const float* inrow = x + (((long)b * res + yy) * res) * C + c;
+      const float* drow = dout + (((long)b * res + y) * res) * C + c;
+      float4 win[7];  // win[kx] = in[x + kx - 3]
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const int xx = k - 3;
+        win[k] = (xx >= 0 && xx < res) ? *reinterpret_cast<const float4*>(inrow + (long)xx * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int xq = 0; xq < res; ++xq) {
+        const float4 d = *reinterpret_cast<const float4*>(drow + (long)xq * C);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          acc[k].x = fmaf(d.x, win[k].x, acc[k].x); acc[k].y = fmaf(d.y, win[k].y, acc[k].y);
+          acc[k].z = fmaf(d.z, win[k].z, acc[k].z); acc[k].w = fmaf(d.w, win[k].w, acc[k].w);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
+        const int xn = xq + 4;
+        win[6] = (xn < res) ? *reinterpret_cast<const float4*>(inrow + (long)xn * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      atomicAdd(&sred[(k * 4 + 0) * c4n + c4], acc[k].x);
+      atomicAdd(&sred[(k * 4 + 1) * c4n + c4], acc[k].y);
+      atomicAdd(&sred[(k * 4 + 2) * c4n + c4], acc[k].z);
+      atomicAdd(&sred[(k * 4 + 3) * c4n + c4], acc[k].w);
+    }
   }
-  atomicAdd(g_w + (c + 0) * 49 + tap, acc.x);
-  atomicAdd(g_w + (c + 1) * 49 + tap, acc.y);
-  atomicAdd(g_w + (c + 2) * 49 + tap, acc.z);
-  atomicAdd(g_w + (c + 3) * 49 + tap, acc.w);
+  __syncthreads();
+  for (int k = threadIdx.x; k < 28 * c4n; k += blockDim.x) {
+    const int q = k / c4n, cc4 = k - q * c4n;
+    const int kx = q >> 2, cj = q & 3;
+    atomicAdd(g_w + (cc4 * 4 + cj) * 49 + ky * 7 + kx, sred[k]);
+  }
 }
 
 // ---- patch recovery tail: pixel shuffle of the transposed-conv GEMM output + 5x5 mixing conv -----------
 // D: [B*(H/ps)*(W/ps), OC*ps*ps] fp32 token-major, column n = (oc, di, dj)  (ConvTranspose2d k=s=ps)
-__device__ __forceinline__ float shuffled(const float* __restrict__ D, int b, int c, int y, int x, int H, int W, int OC,
-                                          int ps) {
-  const int gw = W / ps;
-  return D[(((long)b * (H / ps) + y / ps) * gw + x / ps) * (OC * ps * ps) + (c * ps + (y % ps)) * ps + (x % ps)];
-}
-// pred[b,o,y,x] = sum_{i,dy,dx} P[b,i,y+dy-2,x+dx-2] * w[o,i,dy,dx] (+ residual input) ; masked -> labels
-__global__ void conv5_fwd_kernel(const float* __restrict__ D, const float* __restrict__ w, const float* __restrict__ resid,
-                                 int resid_channels, const float* __restrict__ labels, const uint8_t* __restrict__ mask,
-                                 int mask_mode, float* __restrict__ pred, int B, int OC, int H, int W, int ps) {
+// P: planar [B, OC, H, W] fp32 (the ConvTranspose2d output of the reference, model.py:645)
+__global__ void unshuffle_kernel(const float* __restrict__ D, float* __restrict__ P, int B, int OC, int H, int W, int ps) {
   const long total = (long)B * OC * H * W;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -221,87 +267,146 @@ __global__ void conv5_fwd_kernel(const float* __restrict__ D, const float* __res
   long t = i / W;
   const int y = (int)(t % H);
   t /= H;
-  const int o = (int)(t % OC);
+  const int c = (int)(t % OC);
   const int b = (int)(t / OC);
-  float acc = 0.f;
-  for (int ic = 0; ic < OC; ++ic)
-    for (int dy = 0; dy < 5; ++dy) {
-      const int yy = y + dy - 2;
-      if (yy < 0 || yy >= H) continue;
-      for (int dx = 0; dx < 5; ++dx) {
-        const int xx = x + dx - 2;
-        if (xx < 0 || xx >= W) continue;
-        acc = fmaf(shuffled(D, b, ic, yy, xx, H, W, OC, ps), w[((o * OC + ic) * 5 + dy) * 5 + dx], acc);
-      }
-    }
-  if (resid != nullptr) acc += resid[(((long)b * resid_channels + o) * H + y) * W + x];
-  if (mask_mode == 1 && mask[b * OC + o]) acc = labels[i];
-  if (mask_mode == 2 && mask[i]) acc = labels[i];
-  pred[i] = acc;
+  P[i] = D[(((long)b * (H / ps) + y / ps) * (W / ps) + x / ps) * (OC * ps * ps) + (c * ps + (y % ps)) * ps + (x % ps)];
 }
-// dD[token, (ic,di,dj)] (bf16) = sum_{o,dy,dx} dpred[b,o,y-dy+2,x-dx+2] * w[o,ic,dy,dx]; also column sums per ic
-__global__ void conv5_bwd_data_kernel(const float* __restrict__ dpred, const float* __restrict__ w, bf16* __restrict__ dD,
-                                      float* __restrict__ g_bias, int B, int OC, int H, int W, int ps) {
+// planar gradient -> token-major bf16 [tokens, OC*ps*ps] + ConvTranspose2d bias gradient (sum per channel)
+__global__ void shuffle_grad_kernel(const float* __restrict__ dP, bf16* __restrict__ dD, float* __restrict__ g_bias, int B,
+                                    int OC, int H, int W, int ps) {
   const long total = (long)B * OC * H * W;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   float val = 0.f;
-  int ic = 0;
+  int c = 0;
   if (i < total) {
     const int x = (int)(i % W);
     long t = i / W;
     const int y = (int)(t % H);
     t /= H;
-    ic = (int)(t % OC);
+    c = (int)(t % OC);
     const int b = (int)(t / OC);
-    float acc = 0.f;
-    for (int o = 0; o < OC; ++o)
-      for (int dy = 0; dy < 5; ++dy) {
-        const int yy = y - dy + 2;
-        if (yy < 0 || yy >= H) continue;
-        for (int dx = 0; dx < 5; ++dx) {
-          const int xx = x - dx + 2;
-          if (xx < 0 || xx >= W) continue;
-          acc = fmaf(dpred[(((long)b * OC + o) * H + yy) * W + xx], w[((o * OC + ic) * 5 + dy) * 5 + dx], acc);
-        }
-      }
-    const int gw = W / ps;
-    const bf16 r = __float2bfloat16_rn(acc);
-    dD[(((long)b * (H / ps) + y / ps) * gw + x / ps) * (OC * ps * ps) + (ic * ps + (y % ps)) * ps + (x % ps)] = r;
+    const bf16 r = __float2bfloat16_rn(dP[i]);
+    dD[(((long)b * (H / ps) + y / ps) * (W / ps) + x / ps) * (OC * ps * ps) + (c * ps + (y % ps)) * ps + (x % ps)] = r;
     val = __bfloat162float(r);
   }
-  // all threads of a block share (b, ic) when H*W is a multiple of the block size: block-reduce the bias grad
+  // H*W is a multiple of the block size, so a block never straddles two channels
   __shared__ float sred[kThreads / 32];
   val = warp_sum(val);
   if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = val;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int k = 0; k < kThreads / 32; ++k) s += sred[k];
-    if (i < total) atomicAdd(g_bias + ic, s);
+  if (threadIdx.x == 0 && i < total) {
+    float sacc = 0.f;
+    for (int k = 0; k < kThreads / 32; ++k) sacc += sred[k];
+    atomicAdd(g_bias + c, sacc);
   }
 }
-// g_w[o,ic,dy,dx] += sum_{b,y,x} dpred[b,o,y,x] * P[b,ic,y+dy-2,x+dx-2]
-// one thread per (o,ic,dy,dx); blockIdx.x = chunk of (b, y) rows
-__global__ void conv5_wgrad_kernel(const float* __restrict__ D, const float* __restrict__ dpred, float* __restrict__ g_w,
-                                   int B, int OC, int H, int W, int ps, int rows_per_block) {
-  const int nw = OC * OC * 25;
-  const int tix = threadIdx.x;
-  if (tix >= nw) return;
-  const int dx = tix % 5, dy = (tix / 5) % 5, ic = (tix / 25) % OC, o = tix / (25 * OC);
-  const long r0 = (long)blockIdx.x * rows_per_block;
-  float acc = 0.f;
-  for (long r = r0; r < r0 + rows_per_block && r < (long)B * H; ++r) {
-    const int b = (int)(r / H), y = (int)(r % H);
-    const int yy = y + dy - 2;
-    if (yy < 0 || yy >= H) continue;
-    const float* dp = dpred + (((long)b * OC + o) * H + y) * W;
-    for (int x = 0; x < W; ++x) {
-      const int xx = x + dx - 2;
-      if (xx < 0 || xx >= W) continue;
-      acc = fmaf(dp[x], shuffled(D, b, ic, yy, xx, H, W, OC, ps), acc);
+
+constexpr int C5_TW = 64, C5_TH = 16;  // output tile
+// out[b,o,y,x] = sum_{i,dy,dx} in[b,i,y+dy-2,x+dx-2] * w[o,i,dy,dx]                    (TRANSPOSE=false, forward)
+// out[b,i,y,x] = sum_{o,dy,dx} in[b,o,y-dy+2,x-dx+2] * w[o,i,dy,dx]                    (TRANSPOSE=true, data gradient)
+// 256 threads = 16 x-groups (4 pixels) x 16 rows; halo tile of all channels in smem; per (channel, filter row)
+// 8 smem loads feed 4*5*OC FMAs.
+template <int OC, bool TRANSPOSE>
+__global__ void __launch_bounds__(256)
+conv5_tiled_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ resid,
+                   int resid_channels, const float* __restrict__ labels, const uint8_t* __restrict__ mask, int mask_mode,
+                   float* __restrict__ out, int B, int H, int W) {
+  __shared__ float tile[OC][C5_TH + 4][C5_TW + 4];
+  __shared__ float sw[OC * OC * 25];  // sw[(oo*OC + ii)*25 + dy*5 + dx], already transposed/flipped if TRANSPOSE
+  const int b = blockIdx.z;
+  const int ty0 = blockIdx.y * C5_TH, tx0 = blockIdx.x * C5_TW;
+  for (int k = threadIdx.x; k < OC * OC * 25; k += 256) {
+    if (!TRANSPOSE) {
+      sw[k] = w[k];
+    } else {
+      const int tap = k % 25, ii = (k / 25) % OC, oo = k / (25 * OC);  // output channel oo of this pass = input ch of w
+      sw[k] = w[(ii * OC + oo) * 25 + (24 - tap)];
     }
   }
-  atomicAdd(g_w + tix, acc);
+  for (int k = threadIdx.x; k < OC * (C5_TH + 4) * (C5_TW + 4); k += 256) {
+    const int xx = k % (C5_TW + 4), yy = (k / (C5_TW + 4)) % (C5_TH + 4), c = k / ((C5_TW + 4) * (C5_TH + 4));
+    const int gy = ty0 + yy - 2, gx = tx0 + xx - 2;
+    tile[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? in[(((long)b * OC + c) * H + gy) * W + gx] : 0.f;
+  }
+  __syncthreads();
+  const int lx = (threadIdx.x & 15) * 4, ly = threadIdx.x >> 4;
+  float acc[OC][4];
+#pragma unroll
+  for (int o = 0; o < OC; ++o) acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.f;
+#pragma unroll 1
+  for (int ic = 0; ic < OC; ++ic) {
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = tile[ic][ly + dy][lx + k];
+#pragma unroll
+      for (int o = 0; o < OC; ++o) {
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+          const float ww = sw[(o * OC + ic) * 25 + dy * 5 + dx];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[o][k] = fmaf(v[k + dx], ww, acc[o][k]);
+        }
+      }
+    }
+  }
+  const int gy = ty0 + ly;
+  if (gy >= H) return;
+#pragma unroll
+  for (int o = 0; o < OC; ++o) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int gx = tx0 + lx + k;
+      if (gx >= W) continue;
+      const long idx = (((long)b * OC + o) * H + gy) * W + gx;
+      float r = acc[o][k];
+      if (!TRANSPOSE) {
+        if (resid != nullptr) r += resid[(((long)b * resid_channels + o) * H + gy) * W + gx];
+        if (mask_mode == 1 && mask[b * OC + o]) r = labels[idx];
+        if (mask_mode == 2 && mask[idx]) r = labels[idx];
+      }
+      out[idx] = r;
+    }
+  }
+}
+// g_w[o,ic,dy,dx] += sum_{b,y,x} dpred[b,o,y,x] * P[b,ic,y+dy-2,x+dx-2]; one thread per weight, tiles in smem
+constexpr int C5W_TW = 32, C5W_TH = 16;  // smaller tile for the weight gradient (two tiles in smem)
+template <int OC>
+__global__ void __launch_bounds__(((OC * OC * 25 + 31) / 32) * 32)
+conv5_wgrad_tiled_kernel(const float* __restrict__ P, const float* __restrict__ dpred, float* __restrict__ g_w, int B, int H,
+                         int W) {
+  __shared__ float tp[OC][C5W_TH + 4][C5W_TW + 4];
+  __shared__ float td[OC][C5W_TH][C5W_TW];
+  const int nthr = ((OC * OC * 25 + 31) / 32) * 32;
+  const int tix = threadIdx.x;
+  const int dx = tix % 5, dy = (tix / 5) % 5, ic = (tix / 25) % OC, o = tix / (25 * OC);
+  float acc = 0.f;
+  const int tiles_x = W / C5W_TW, tiles_y = H / C5W_TH;
+  // each block sweeps a few tiles so that the final atomics are amortised
+  for (int tile_id = blockIdx.x; tile_id < B * tiles_x * tiles_y; tile_id += gridDim.x) {
+    const int b = tile_id / (tiles_x * tiles_y);
+    const int tr = tile_id % (tiles_x * tiles_y);
+    const int ty0 = (tr / tiles_x) * C5W_TH, tx0 = (tr % tiles_x) * C5W_TW;
+    __syncthreads();
+    for (int k = tix; k < OC * (C5W_TH + 4) * (C5W_TW + 4); k += nthr) {
+      const int xx = k % (C5W_TW + 4), yy = (k / (C5W_TW + 4)) % (C5W_TH + 4), c = k / ((C5W_TW + 4) * (C5W_TH + 4));
+      const int gy = ty0 + yy - 2, gx = tx0 + xx - 2;
+      tp[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? P[(((long)b * OC + c) * H + gy) * W + gx] : 0.f;
+    }
+    for (int k = tix; k < OC * C5W_TH * C5W_TW; k += nthr) {
+      const int xx = k % C5W_TW, yy = (k / C5W_TW) % C5W_TH, c = k / (C5W_TW * C5W_TH);
+      td[c][yy][xx] = dpred[(((long)b * OC + c) * H + ty0 + yy) * W + tx0 + xx];
+    }
+    __syncthreads();
+    if (tix < OC * OC * 25) {
+      for (int y = 0; y < C5W_TH; ++y) {
+#pragma unroll 8
+        for (int x = 0; x < C5W_TW; ++x) acc = fmaf(td[o][y][x], tp[ic][y + dy][x + dx], acc);
+      }
+    }
+  }
+  if (tix < OC * OC * 25) atomicAdd(g_w + tix, acc);
 }
 
 // ---- loss (scOT/model.py:1425-1484) --------------------------------------------------------------------
@@ -431,38 +536,66 @@ int scot_scale_add_bwd_launch(const float* g, const void* zb, const float* gamma
 }
 int scot_dwconv7_fwd_launch(const float* x, const float* w, const float* bias, float* out, int B, int res, int C,
                             cudaStream_t st) {
-  dwconv7_kernel<false><<<blocks_for((long)B * res * res * (C / 4)), kThreads, 0, st>>>(x, w, bias, nullptr, out, B, res, C);
+  const long total = (long)B * res * ((res + 7) / 8) * (C / 4);
+  dwconv7_kernel<false><<<blocks_for(total, 128), 128, 0, st>>>(x, w, bias, nullptr, out, B, res, C);
   SCOT_LAUNCH_CHECK();
   return 0;
 }
 int scot_dwconv7_bwd_launch(const float* x, const float* w, const float* dout, const float* g_in, float* g_out, float* g_w,
                             int B, int res, int C, cudaStream_t st) {
-  dwconv7_kernel<true><<<blocks_for((long)B * res * res * (C / 4)), kThreads, 0, st>>>(dout, w, nullptr, g_in, g_out, B, res, C);
+  const long total = (long)B * res * ((res + 7) / 8) * (C / 4);
+  dwconv7_kernel<true><<<blocks_for(total, 128), 128, 0, st>>>(dout, w, nullptr, g_in, g_out, B, res, C);
   SCOT_LAUNCH_CHECK();
-  const long npix = (long)B * res * res;
-  const int ppb = 512;
-  dwconv7_wgrad_kernel<<<dim3((C + 15) / 16, (unsigned)((npix + ppb - 1) / ppb)), 256, 0, st>>>(x, dout, g_w, B, res, C, ppb);
+  const int c4n = C / 4;
+  SCOT_REQUIRE(c4n <= 256, "dwconv7: at most 1024 channels");
+  // images per block so that ~2 blocks per SM exist for each of the 7 filter rows
+  int ipb = (B * 7 + 295) / 296;
+  if (ipb < 1) ipb = 1;
+  const size_t smem = (size_t)28 * c4n * sizeof(float);
+  dwconv7_wgrad_kernel<<<dim3(7, (B + ipb - 1) / ipb), 256, smem, st>>>(x, dout, g_w, B, res, C, ipb);
   SCOT_LAUNCH_CHECK();
   return 0;
 }
-int scot_conv5_fwd_launch(const float* D, const float* w, const float* resid, int resid_channels, const float* labels,
-                          const uint8_t* mask, int mask_mode, float* pred, int B, int OC, int H, int W, int ps,
-                          cudaStream_t st) {
+
+#define C5_DISPATCH(OCV, CALL) \
+  case OCV: { CALL; break; }
+
+int scot_unshuffle_launch(const float* D, float* P, int B, int OC, int H, int W, int ps, cudaStream_t st) {
+  unshuffle_kernel<<<blocks_for((long)B * OC * H * W), kThreads, 0, st>>>(D, P, B, OC, H, W, ps);
+  SCOT_LAUNCH_CHECK();
+  return 0;
+}
+int scot_conv5_fwd_launch(const float* P, const float* w, const float* resid, int resid_channels, const float* labels,
+                          const uint8_t* mask, int mask_mode, float* pred, int B, int OC, int H, int W, cudaStream_t st) {
   SCOT_REQUIRE(mask_mode == 0 || (mask != nullptr && labels != nullptr), "conv5_fwd: mask needs labels");
-  conv5_fwd_kernel<<<blocks_for((long)B * OC * H * W), kThreads, 0, st>>>(D, w, resid, resid_channels, labels, mask, mask_mode,
-                                                                        pred, B, OC, H, W, ps);
+  SCOT_REQUIRE(OC >= 1 && OC <= 6, "conv5: 1..6 output channels supported");
+  dim3 grid((W + C5_TW - 1) / C5_TW, (H + C5_TH - 1) / C5_TH, B);
+  switch (OC) {
+#define C5F(N) C5_DISPATCH(N, (conv5_tiled_kernel<N, false><<<grid, 256, 0, st>>>(P, w, resid, resid_channels, labels, mask, mask_mode, pred, B, H, W)))
+    C5F(1) C5F(2) C5F(3) C5F(4) C5F(5) C5F(6)
+#undef C5F
+  }
   SCOT_LAUNCH_CHECK();
   return 0;
 }
-int scot_conv5_bwd_launch(const float* D, const float* w, const float* dpred, void* dD, float* g_w, float* g_bias, int B,
-                          int OC, int H, int W, int ps, cudaStream_t st) {
+// dP_scratch: planar fp32 [B,OC,H,W] scratch for the data gradient before it is shuffled to token-major bf16
+int scot_conv5_bwd_launch(const float* P, const float* w, const float* dpred, float* dP_scratch, void* dD, float* g_w,
+                          float* g_bias, int B, int OC, int H, int W, int ps, cudaStream_t st) {
   SCOT_REQUIRE((H * W) % kThreads == 0, "conv5_bwd: H*W must be a multiple of %d", kThreads);
-  SCOT_REQUIRE(OC * OC * 25 <= 1024, "conv5_bwd: at most 6 output channels supported");
-  conv5_bwd_data_kernel<<<blocks_for((long)B * OC * H * W), kThreads, 0, st>>>(dpred, w, (bf16*)dD, g_bias, B, OC, H, W, ps);
+  SCOT_REQUIRE(OC >= 1 && OC <= 6, "conv5: 1..6 output channels supported");
+  SCOT_REQUIRE(H % C5W_TH == 0 && W % C5W_TW == 0, "conv5_bwd: image size must be a multiple of %dx%d", C5W_TW, C5W_TH);
+  dim3 grid((W + C5_TW - 1) / C5_TW, (H + C5_TH - 1) / C5_TH, B);
+  const int tiles = B * (W / C5W_TW) * (H / C5W_TH);
+  const int wg_blocks = tiles < 592 ? tiles : 592;
+  switch (OC) {
+#define C5B(N) C5_DISPATCH(N, (conv5_tiled_kernel<N, true><<<grid, 256, 0, st>>>(dpred, w, nullptr, 0, nullptr, nullptr, 0, dP_scratch, B, H, W)); \
+                             scot_count_launch(); \
+                             (conv5_wgrad_tiled_kernel<N><<<wg_blocks, ((N * N * 25 + 31) / 32) * 32, 0, st>>>(P, dpred, g_w, B, H, W)))
+    C5B(1) C5B(2) C5B(3) C5B(4) C5B(5) C5B(6)
+#undef C5B
+  }
   SCOT_LAUNCH_CHECK();
-  const int rpb = 16;
-  const int nthr = ((OC * OC * 25 + 31) / 32) * 32;
-  conv5_wgrad_kernel<<<(unsigned)(((long)B * H + rpb - 1) / rpb), nthr, 0, st>>>(D, dpred, g_w, B, OC, H, W, ps, rpb);
+  shuffle_grad_kernel<<<blocks_for((long)B * OC * H * W), kThreads, 0, st>>>(dP_scratch, (bf16*)dD, g_bias, B, OC, H, W, ps);
   SCOT_LAUNCH_CHECK();
   return 0;
 }

@@ -217,9 +217,9 @@ def test_window_attention_forward_backward(L, case):
     w2 = torch.randn(heads, 512, device=dev) / 512 ** 0.5
     ls = math.log(10.0) + 0.3 * torch.randn(heads, 1, 1, device=dev)
     R = (2 * ws - 1) ** 2
-    tab2 = torch.empty(R, heads, device=dev)
-    alpha = torch.empty(heads, device=dev)
-    L.cpb_fwd(w1, b1, w2, ls, tab2, alpha, ws, heads)
+    cpb = L.CpbLayerBuffers(w1, b1, w2, ls, ws, heads)
+    cpb.forward()
+    tab2, alpha = cpb.tab2, cpb.alpha
     coords = O.relative_coords_table(ws).to(dev)
     tab_ref = 16 * torch.sigmoid(F.linear(F.relu(F.linear(coords, w1, b1)), w2)) * math.log2(math.e)
     assert rel(tab2, tab_ref) < 1e-5
@@ -239,8 +239,7 @@ def test_window_attention_forward_backward(L, case):
     import ctypes
     pbytes = L.load().scot_attn_bwd_partial_bytes(ws, heads, nwin)
     partial = torch.empty(pbytes // 4, device=dev)
-    dtab = torch.zeros(R, heads, device=dev)
-    dalpha = torch.zeros(heads, device=dev)
+    dtab, dalpha = cpb.dtab, cpb.dalpha
     gq = torch.zeros(C, device=dev)
     gv = torch.zeros(C, device=dev)
     L.attn_bwd(qkv, out, d_o, lse, tab2, alpha, dqkv, partial, dtab, dalpha, gq, gv, Bn, res, ws, shift, heads, hd)
@@ -250,9 +249,8 @@ def test_window_attention_forward_backward(L, case):
     assert rel(dqkv[:, C:2 * C].float(), g_ref[:, C:2 * C]) < 3e-2, "dk"
     assert rel(gq, dqkv[:, :C].float().sum(0)) < 1e-3 and rel(gv, dqkv[:, 2 * C:].float().sum(0)) < 1e-3
     # bias-table / logit-scale gradients through the two-stage reduction + cpb backward
-    dpre = torch.empty(R * heads, device=dev)
-    g1, gb, g2, gls = (torch.zeros_like(w1), torch.zeros_like(b1), torch.zeros_like(w2), torch.zeros(heads, device=dev))
-    L.cpb_bwd(w1, b1, w2, ls, dtab, dalpha, dpre, g1, gb, g2, gls, ws, heads)
+    cpb.backward()
+    g1, gb, g2, gls = cpb.grad(0, w1.shape), cpb.grad(1, b1.shape), cpb.grad(2, w2.shape), cpb.grad(3, (heads,))
     assert rel(g2, leaves[3].grad) < 3e-2, "cpb w2 grad"
     assert rel(g1, leaves[1].grad) < 3e-2, "cpb w1 grad"
     assert rel(gb, leaves[2].grad) < 3e-2, "cpb b1 grad"
