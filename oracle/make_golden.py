@@ -30,11 +30,11 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 CONFIGS = {
     # small 3-stage model: stage 0 shifted 8x8 windows on a 16x16 grid, stage 1 one 8x8 window, stage 2 4x4
-    "tiny": dict(cfg=dict(image_size=64, patch_size=4, num_channels=3, num_out_channels=3, embed_dim=16,
-                          depths=[2, 2, 2], num_heads=[1, 2, 4], skip_connections=[1, 1, 0], window_size=8,
+    "tiny": dict(cfg=dict(image_size=64, patch_size=4, num_channels=3, num_out_channels=3, embed_dim=32,
+                          depths=[2, 2, 2], num_heads=[2, 4, 8], skip_connections=[1, 1, 0], window_size=8,
                           mlp_ratio=4.0, drop_path_rate=0.0, use_conditioning=True, p=1,
                           channel_slice_list_normalized_loss=[0, 1, 3], residual_model="convnext"),
-                 batch=2, mask_channels=(2,), store_all=True),
+                 batch=2, mask_channels=(2,), store_all=False),
     # same but unconditioned LayerNorm, plain l1 loss, learn_residual off, no pixel mask
     "tiny_ln": dict(cfg=dict(image_size=64, patch_size=4, num_channels=2, num_out_channels=2, embed_dim=32,
                              depths=[2, 2, 2], num_heads=[2, 4, 8], skip_connections=[1, 0, 0], window_size=8,

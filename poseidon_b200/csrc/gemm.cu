@@ -228,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (r0 < RPP && col < N) {
         const float4 bias = ep.bias != nullptr ? *reinterpret_cast<const float4*>(ep.bias + col)
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-        constexpr int U = 4;  // rows in flight per thread (independent global loads issued back to back)
+        constexpr int U = 8;  // rows in flight per thread (independent global loads issued back to back)
         for (int r = r0; r < BM; r += RPP * U) {
           float4 v[U], aux[U];
           bool ok[U];
