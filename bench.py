@@ -271,10 +271,14 @@ def main():
     for p in model.parameters():
         p.grad = None
 
+    dx, dy, dt = (torch.empty_like(hx, device=dev), torch.empty_like(hy, device=dev), torch.empty_like(ht, device=dev))
+
     def e2e_step():
-        x = hx.to(dev, non_blocking=True)
-        y = hy.to(dev, non_blocking=True)
-        t = ht.to(dev, non_blocking=True)
+        # host (pinned) -> device copies of this step's batch into the loader's device buffers
+        dx.copy_(hx, non_blocking=True)
+        dy.copy_(hy, non_blocking=True)
+        dt.copy_(ht, non_blocking=True)
+        x, y, t = dx, dy, dt
         model.flat_gradients.zero_()
         out = model(pixel_values=x, time=t, labels=y)
         out.loss.backward()

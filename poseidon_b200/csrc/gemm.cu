@@ -9,11 +9,16 @@
 // and their autograd backward (dgrad: B operand MN-major = the same weight read transposed;
 // wgrad: both operands MN-major with the token dimension as the reduction, split over CTAs).
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0      : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
-//   warps 2..5  : epilogue: tcgen05.ld (32x32b) -> registers -> fp32 staging in (re-used) pipeline smem
-//                 -> coalesced 128-bit global stores with the fused op (bias / GELU / GELU' / RMW / red.add)
+// Structure: persistent kernel, one CTA per SM looping over 128 x BN output tiles, 320 threads:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx); the smem ring
+//                 runs ahead across tile boundaries, so operand loads of tile i+1 overlap the epilogue of tile i
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1) into one
+//                 of TWO accumulator buffers in TMEM (tmem_full / tmem_empty mbarriers)
+//   warps 2..9  : epilogue: prefetch the auxiliary global operand (residual / saved pre-activation) while the MMAs
+//                 run, tcgen05.ld (32x32b) -> fp32 staging smem -> coalesced 128-bit global stores with the fused
+//                 op (bias / GELU / GELU' / RMW / red.add)
+// These GEMMs have K = 96..3072 and are HBM/epilogue bound, so the design goal is to hide every fixed latency
+// (TMA round trip, TMEM allocation, store drain) behind the epilogue rather than to saturate the tensor pipe.
 // Tails in M, N and K are handled by TMA out-of-bounds zero fill + predicated stores.
 #include "common.cuh"
 #include "scot_b200.h"
@@ -23,8 +28,8 @@ namespace {
 constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 64;        // bf16 elements per k-block = one 128B swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int GEMM_THREADS = 320;
+constexpr int EPI_THREADS = 256;
 
 struct EpiArgs {
   const float* bias;
@@ -102,7 +107,8 @@ __device__ __forceinline__ void epi_store(const EpiArgs& ep, long row, int col, 
 // =================================================================================================
 template <int BN>
 struct TileCfg {
-  static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // one accumulator buffer
+  static constexpr int kTmemCols = 2 * kAccCols;                                           // double buffered
   static constexpr int kABytes = BM * BK * 2;  // 16 KB
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -111,26 +117,26 @@ struct TileCfg {
 };
 
 template <int BN, int AMN, int BMN, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-               int kblocks_total, int kblocks_per_split, int num_stages, EpiArgs ep) {
+               int kblocks_total, int kblocks_per_split, int tiles_m, int tiles_n, int total_tiles, int num_stages,
+               EpiArgs ep) {
   using Cfg = TileCfg<BN>;
+  static_assert(BN % 64 == 0 || BMN == 0, "MN-major B needs 64-wide atoms");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [0,1024) barriers + tmem ptr ; then 1024-aligned stages
+  // carve: [0,1024) barriers + tmem ptr ; 1024-aligned operand stages ; fp32 staging tile for the epilogue
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + 8;
-  uint64_t* tmem_full_bar = empty_bar + 8;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + 8;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint8_t* tiles = smem + 1024;
+  float* stage = reinterpret_cast<float*>(tiles + (size_t)num_stages * Cfg::kStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
-  const int kb_begin = blockIdx.z * kblocks_per_split;
-  const int kb_end = min(kb_begin + kblocks_per_split, kblocks_total);
-  const int nkb = kb_end - kb_begin;
+  const int tiles_mn = tiles_m * tiles_n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -139,7 +145,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], EPI_THREADS);
+    }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
@@ -151,25 +160,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % num_stages;
-        const uint32_t ph = (uint32_t)(i / num_stages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        uint8_t* sa = tiles + (size_t)s * Cfg::kStageBytes;
-        uint8_t* sb = sa + Cfg::kABytes;
-        const int k0 = (kb_begin + i) * BK;
-        if constexpr (AMN == 0) {
-          tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {64 k, 128 rows}
-        } else {
+      int it = 0;  // running k-block counter over all my tiles (ring position)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn, rem = t - split * tiles_mn;
+        const int m0 = (rem % tiles_m) * BM, n0 = (rem / tiles_m) * BN;  // m fastest: a CTA stays in one column block
+        const int kb_begin = split * kblocks_per_split;
+        const int kb_end = min(kb_begin + kblocks_per_split, kblocks_total);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % num_stages;
+          const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          uint8_t* sa = tiles + (size_t)s * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const int k0 = kb * BK;
+          if constexpr (AMN == 0) {
+            tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {64 k, 128 rows}
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], m0 + 64 * j, k0);
-        }
-        if constexpr (BMN == 0) {
-          tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {64 k, BN rows}
-        } else {
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], m0 + 64 * j, k0);
+          }
+          if constexpr (BMN == 0) {
+            tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {64 k, BN rows}
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + 64 * j, k0);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + 64 * j, k0);
+          }
         }
       }
     }
@@ -177,80 +193,109 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, AMN, BMN);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % num_stages;
-        const uint32_t ph = (uint32_t)(i / num_stages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const int split = t / tiles_mn;
+        const int kb_begin = split * kblocks_per_split;
+        const int nkb = min(kb_begin + kblocks_per_split, kblocks_total) - kb_begin;
+        const int buf = lt & 1;
+        mbar_wait(&tmem_empty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(tiles + (size_t)s * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::kAccCols);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % num_stages;
+          const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)s * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major: advance 16 elements = 32 B inside the swizzle atom. MN-major: advance 16 k-rows = 2048 B.
-          const uint64_t da = (AMN == 0) ? umma_smem_desc(sa + k * 32, 16, 1024)
-                                         : umma_smem_desc(sa + k * 2048, BK * 128, 1024);
-          const uint64_t db = (BMN == 0) ? umma_smem_desc(sb + k * 32, 16, 1024)
-                                         : umma_smem_desc(sb + k * 2048, BK * 128, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: advance 16 elements = 32 B inside the swizzle atom. MN-major: advance 16 k-rows = 2048 B.
+            const uint64_t da = (AMN == 0) ? umma_smem_desc(sa + k * 32, 16, 1024)
+                                           : umma_smem_desc(sa + k * 2048, BK * 128, 1024);
+            const uint64_t db = (BMN == 0) ? umma_smem_desc(sb + k * 32, 16, 1024)
+                                           : umma_smem_desc(sb + k * 2048, BK * 128, 1024);
+            umma_bf16(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
         }
-        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+        umma_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ------------------------------ epilogue ------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int et = (warp - 2) * 32 + lane;
-    float* stage = reinterpret_cast<float*>(tiles);
-    if (nkb > 0) {
-      mbar_wait(tmem_full_bar, 0);
+    // ------------------------------ epilogue (8 warps) ------------------------------
+    const int ew = warp - 2;             // 0..7
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = ew >> 2;            // column half handled in phase 1
+    const int et = ew * 32 + lane;       // 0..255
+    constexpr int VPR = BN / 4;              // float4 per tile row
+    constexpr int RPP = EPI_THREADS / VPR;   // rows per pass
+    constexpr int NPASS = (BM + RPP - 1) / RPP;
+    constexpr bool kHasAux = (MODE == SCOT_EPI_GELU_BWD || MODE == SCOT_EPI_RMW_F32 || MODE == SCOT_EPI_ADD_F32_BF16);
+    constexpr int NCHUNK = BN / 32;          // 32-column TMEM chunks; warps 2-5 take the even ones, 6-9 the odd ones
+    const int cv = et % VPR;
+    const int r0 = et / VPR;
+    const bool active = r0 < RPP;
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+    int lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const int split = t / tiles_mn, rem = t - split * tiles_mn;
+      const int m0 = (rem % tiles_m) * BM, n0 = (rem / tiles_m) * BN;
+      const int col = n0 + cv * 4;
+      const bool col_ok = active && col < N;
+      // prefetch the auxiliary operand of this tile (its addresses do not depend on the accumulators)
+      float4 aux[kHasAux ? NPASS : 1];
+      if constexpr (kHasAux) {
+#pragma unroll
+        for (int p = 0; p < NPASS; ++p) {
+          const int r = r0 + p * RPP;
+          if (col_ok && r < BM && (long)m0 + r < M) aux[p] = epi_load_aux<MODE>(ep, (long)m0 + r, col);
+        }
+      }
+      const int buf = lt & 1;
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
       tc_fence_after();
-      const int r = q * 32 + lane;
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // previous tile's phase 2 is done with `stage`
+      {
+        const int r = q * 32 + lane;
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::kAccCols) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(stage + (size_t)r * Cfg::kStagePitch + c);
+        for (int ci = 0; ci < NCHUNK; ++ci) {
+          if ((ci & 1) == half) {
+            float v[32];
+            tmem_ld_32x32(tacc + (uint32_t)(ci * 32), v);
+            tmem_ld_wait();
+            float4* dst = reinterpret_cast<float4*>(stage + (size_t)r * Cfg::kStagePitch + ci * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
       }
       tc_fence_before();
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-    if (nkb > 0) {
-      constexpr int VPR = BN / 4;              // float4 per tile row
-      constexpr int RPP = EPI_THREADS / VPR;   // rows per pass
-      const int cv = et % VPR;
-      const int r0 = et / VPR;
-      const int col = n0 + cv * 4;
-      float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r0 < RPP && col < N) {
+      mbar_arrive(&tmem_empty_bar[buf]);  // this thread no longer reads the accumulator buffer
+      asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");  // staging tile complete
+      if (col_ok) {
         const float4 bias = ep.bias != nullptr ? *reinterpret_cast<const float4*>(ep.bias + col)
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-        constexpr int U = 8;  // rows in flight per thread (independent global loads issued back to back)
-        for (int r = r0; r < BM; r += RPP * U) {
-          float4 v[U], aux[U];
-          bool ok[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int ru = r + u * RPP;
-            ok[u] = ru < BM && (long)m0 + ru < M;
-            if (ok[u]) {
-              aux[u] = epi_load_aux<MODE>(ep, (long)m0 + ru, col);
-              v[u] = *reinterpret_cast<const float4*>(stage + (size_t)ru * Cfg::kStagePitch + cv * 4);
-            }
+        for (int p = 0; p < NPASS; ++p) {
+          const int r = r0 + p * RPP;
+          if (r < BM && (long)m0 + r < M) {
+            const float4 v = *reinterpret_cast<const float4*>(stage + (size_t)r * Cfg::kStagePitch + cv * 4);
+            epi_store<MODE>(ep, (long)m0 + r, col, v, kHasAux ? aux[kHasAux ? p : 0] : make_float4(0.f, 0.f, 0.f, 0.f), bias, csum);
           }
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (ok[u]) epi_store<MODE>(ep, (long)m0 + r + u * RPP, col, v[u], aux[u], bias, csum);
         }
         if constexpr (MODE == SCOT_EPI_GELU_BWD) {
-          if (ep.colsum != nullptr) {
+          // column sums (bias gradient): flush when the next tile of this CTA is in a different column block
+          const int tn = t + gridDim.x;
+          const bool last_of_col = (tn >= total_tiles) || ((tn % tiles_mn) / tiles_m) != (rem / tiles_m);
+          if (last_of_col && ep.colsum != nullptr) {
             atomicAdd(ep.colsum + col + 0, csum.x);
             atomicAdd(ep.colsum + col + 1, csum.y);
             atomicAdd(ep.colsum + col + 2, csum.z);
             atomicAdd(ep.colsum + col + 3, csum.w);
+            csum = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
       }
@@ -348,7 +393,7 @@ int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, in
   const int kblocks = ceil_div(K, BK);
   int splits = 1;
   if (MODE == SCOT_EPI_ATOMIC_F32) {
-    // split the (long) reduction so that the grid covers ~2 waves of the machine
+    // split the (long) reduction so that there are about two tiles of work per SM
     const int target = 2 * g_num_sms;
     splits = target / (tiles_m * tiles_n);
     if (splits < 1) splits = 1;
@@ -356,22 +401,22 @@ int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, in
   }
   int kps = ceil_div(kblocks, splits);
   splits = ceil_div(kblocks, kps);  // no empty split
+  const int total_tiles = tiles_m * tiles_n * splits;
 
-  int min_stages = ceil_div(Cfg::kStagingBytes, Cfg::kStageBytes);
-  int stages = kps < 3 ? kps : 3;  // 3 stages keep two CTAs resident per SM (epilogue of one overlaps loads of the other)
-  if (stages < min_stages) stages = min_stages;
-  if (stages < 2) stages = 2;
-  SCOT_REQUIRE(stages <= 8, "gemm: too many stages");
-  const size_t smem = 1024 /*align slack*/ + 1024 /*barriers*/ + (size_t)stages * Cfg::kStageBytes;
-  SCOT_REQUIRE(smem <= 227 * 1024, "gemm: smem %zu too large", smem);
+  // smem: barriers + operand ring + dedicated fp32 staging tile (the ring keeps running during the epilogue)
+  const size_t fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + (size_t)Cfg::kStagingBytes;
+  int stages = (int)((227 * 1024 - fixed) / Cfg::kStageBytes);
+  if (stages > 6) stages = 6;
+  SCOT_REQUIRE(stages >= 2, "gemm: tile too large for shared memory");
+  const size_t smem = fixed + (size_t)stages * Cfg::kStageBytes;
   auto kern = gemm_tc_kernel<BN, AMN, BMN, MODE>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     SCOT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  dim3 grid(tiles_n, tiles_m, splits);
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, M, N, kblocks, kps, stages, ep);
+  const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, M, N, kblocks, kps, tiles_m, tiles_n, total_tiles, stages, ep);
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -379,7 +424,7 @@ int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, in
 template <int AMN, int BMN, int MODE>
 int dispatch_bn(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
                 cudaStream_t stream) {
-  if (BMN == 0) {
+  if constexpr (BMN == 0) {
     if (N % 128 == 0) return launch_tc<128, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
     if (N % 96 == 0) return launch_tc<96, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
     if (N > 64) return launch_tc<128, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
