@@ -46,8 +46,8 @@ unsigned long long scot_launch_count(void);
 enum {
   SCOT_EPI_BF16 = 0,        /* out0(bf16) = acc + bias                                               */
   SCOT_EPI_F32 = 1,         /* out0(f32)  = acc + bias                                               */
-  SCOT_EPI_GELU = 2,        /* out0(bf16) = h = acc + bias (may be NULL), out1(bf16) = gelu_erf(h)   */
-  SCOT_EPI_GELU_BWD = 3,    /* out0(bf16) = acc * gelu_erf'(aux(bf16)); colsum(f32)[n] += column sums */
+  SCOT_EPI_GELU = 2,        /* h = acc + bias: out0(bf16) = gelu_erf'(h) (may be NULL), out1(bf16) = gelu_erf(h) */
+  SCOT_EPI_GELU_BWD = 3,    /* out0(bf16) = acc * aux(bf16) (aux = saved gelu'); colsum(f32)[n] += column sums */
   SCOT_EPI_RMW_F32 = 4,     /* out0(f32) += acc                                                      */
   SCOT_EPI_ATOMIC_F32 = 5,  /* red.add out0(f32) += acc (split reduction; wgrad)                     */
   SCOT_EPI_ADD_F32_BF16 = 6 /* out0(f32) = acc + bias + aux(f32); out1(bf16, may be NULL) = same     */

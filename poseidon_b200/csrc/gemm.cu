@@ -58,28 +58,37 @@ __device__ __forceinline__ float4 epi_load_aux(const EpiArgs& ep, long row, int 
   }
 }
 
+// (gelu'(x), gelu(x)) as two bf16 in one 32-bit word (low = derivative, high = activation)
+__device__ __forceinline__ float gelu_pack(float x) {
+  float cdf, pdf;
+  gelu_parts(x, cdf, pdf);
+  return __uint_as_float(pack_bf16x2(fmaf(x, pdf, cdf), x * cdf));
+}
+
 template <int MODE>
 __device__ __forceinline__ void epi_store(const EpiArgs& ep, long row, int col, float4 v, float4 aux, float4 bias,
                                           float4& csum) {
-  v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+  if constexpr (MODE != SCOT_EPI_GELU) {
+    v.x += bias.x; v.y += bias.y; v.z += bias.z; v.w += bias.w;
+  }
   if constexpr (MODE == SCOT_EPI_BF16) {
     uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + row * ep.ld0 + col) = o;
   } else if constexpr (MODE == SCOT_EPI_F32) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + row * ep.ld0 + col) = v;
   } else if constexpr (MODE == SCOT_EPI_GELU) {
-    // out0 = pre-activation h (saved for backward), out1 = gelu_erf(h). h is rounded to bf16 first so
-    // that forward and backward see the same pre-activation.
-    float hx = bf16_round(v.x), hy = bf16_round(v.y), hz = bf16_round(v.z), hw = bf16_round(v.w);
-    uint2 o0 = make_uint2(pack_bf16x2(hx, hy), pack_bf16x2(hz, hw));
-    uint2 o1 = make_uint2(pack_bf16x2(gelu_erf(hx), gelu_erf(hy)), pack_bf16x2(gelu_erf(hz), gelu_erf(hw)));
+    // out0 = gelu_erf'(h) (saved for backward, may be NULL), out1 = gelu_erf(h), h = acc + bias.
+    // `v` arrives here already transformed by gelu_pack(): each 32-bit word holds (gelu', gelu) as two bf16.
+    const uint32_t w0 = __float_as_uint(v.x), w1 = __float_as_uint(v.y), w2 = __float_as_uint(v.z), w3 = __float_as_uint(v.w);
+    const uint2 o_grad = make_uint2(__byte_perm(w0, w1, 0x5410), __byte_perm(w2, w3, 0x5410));  // low halves
+    const uint2 o_act = make_uint2(__byte_perm(w0, w1, 0x7632), __byte_perm(w2, w3, 0x7632));   // high halves
     if (ep.out0 != nullptr)
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + row * ep.ld0 + col) = o0;
-    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out1) + row * ep.ld1 + col) = o1;
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + row * ep.ld0 + col) = o_grad;
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out1) + row * ep.ld1 + col) = o_act;
   } else if constexpr (MODE == SCOT_EPI_GELU_BWD) {
-    const float2 h01 = unpack_bf16x2(__float_as_uint(aux.x)), h23 = unpack_bf16x2(__float_as_uint(aux.y));
-    v.x *= gelu_erf_grad(h01.x); v.y *= gelu_erf_grad(h01.y);
-    v.z *= gelu_erf_grad(h23.x); v.w *= gelu_erf_grad(h23.y);
+    // aux = gelu'(h) saved by the forward epilogue: dh = (dy W) * gelu'(h)
+    const float2 g01 = unpack_bf16x2(__float_as_uint(aux.x)), g23 = unpack_bf16x2(__float_as_uint(aux.y));
+    v.x *= g01.x; v.y *= g01.y; v.z *= g23.x; v.w *= g23.y;
     uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + row * ep.ld0 + col) = o;
     const float2 r01 = unpack_bf16x2(o.x), r23 = unpack_bf16x2(o.y);  // column sums of what was stored
@@ -260,15 +269,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       {
         const int r = q * 32 + lane;
         const uint32_t tacc = tmem_base + (uint32_t)(buf * Cfg::kAccCols) + ((uint32_t)(q * 32) << 16);
+        constexpr int MYCH = (NCHUNK + 1) / 2;  // chunks per warp (even ones for warps 2-5, odd ones for 6-9)
+        float v[MYCH][32];
 #pragma unroll
-        for (int ci = 0; ci < NCHUNK; ++ci) {
-          if ((ci & 1) == half) {
-            float v[32];
-            tmem_ld_32x32(tacc + (uint32_t)(ci * 32), v);
-            tmem_ld_wait();
+        for (int k = 0; k < MYCH; ++k) {
+          const int ci = 2 * k + half;
+          if (ci < NCHUNK) tmem_ld_32x32(tacc + (uint32_t)(ci * 32), v[k]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < MYCH; ++k) {
+          const int ci = 2 * k + half;
+          if (ci < NCHUNK) {
+            if constexpr (MODE == SCOT_EPI_GELU) {
+              // 32 independent activations per thread: plenty of ILP for the transcendental path
+              const int cbase = n0 + ci * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float b = (ep.bias != nullptr && cbase + j < N) ? __ldg(ep.bias + cbase + j) : 0.f;
+                v[k][j] = gelu_pack(v[k][j] + b);
+              }
+            }
             float4* dst = reinterpret_cast<float4*>(stage + (size_t)r * Cfg::kStagePitch + ci * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[k][4 * j], v[k][4 * j + 1], v[k][4 * j + 2], v[k][4 * j + 3]);
           }
         }
       }
@@ -329,7 +353,10 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, long lda, int amn, 
   }
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 bias = ep.bias != nullptr ? *reinterpret_cast<const float4*>(ep.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-  epi_store<MODE>(ep, row, col, make_float4(acc[0], acc[1], acc[2], acc[3]), epi_load_aux<MODE>(ep, row, col), bias, csum);
+  float4 vv = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  if constexpr (MODE == SCOT_EPI_GELU)
+    vv = make_float4(gelu_pack(vv.x + bias.x), gelu_pack(vv.y + bias.y), gelu_pack(vv.z + bias.z), gelu_pack(vv.w + bias.w));
+  epi_store<MODE>(ep, row, col, vv, epi_load_aux<MODE>(ep, row, col), bias, csum);
   if constexpr (MODE == SCOT_EPI_GELU_BWD) {
     if (ep.colsum != nullptr) {
       atomicAdd(ep.colsum + col + 0, csum.x);

@@ -68,20 +68,20 @@ def test_gemm_gelu_and_backward(L, impl):
     A = torch.randn(M, K, device=dev).bfloat16()
     B = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
     bias = torch.randn(N, device=dev)
-    h = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    g = torch.empty_like(h)
-    L.gemm(A, B, M, N, K, mode=L.EPI_GELU, bias=bias, out0=h, out1=g, impl=impl)
-    ref = A.float() @ B.float().t() + bias
-    assert rel(h.float(), ref) < 4e-3
-    assert rel(g.float(), F.gelu(h.float())) < 4e-3
+    gp = torch.empty(M, N, device=dev, dtype=torch.bfloat16)  # gelu'(h), saved for backward
+    g = torch.empty_like(gp)
+    L.gemm(A, B, M, N, K, mode=L.EPI_GELU, bias=bias, out0=gp, out1=g, impl=impl)
+    href = (A.float() @ B.float().t() + bias).requires_grad_(True)
+    gref = F.gelu(href)
+    gref.sum().backward()
+    assert rel(g.float(), gref) < 4e-3
+    assert rel(gp.float(), href.grad) < 4e-3
     dY = torch.randn(M, K, device=dev).bfloat16()
     W = (torch.randn(K, N, device=dev) / K ** 0.5).bfloat16()
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     cs = torch.zeros(N, device=dev)
-    L.gemm(dY, W, M, N, K, b_mn=True, mode=L.EPI_GELU_BWD, out0=out, aux=h, colsum=cs, impl=impl)
-    hh = h.float().requires_grad_(True)
-    F.gelu(hh).backward(dY.float() @ W.float())
-    assert rel(out.float(), hh.grad) < 4e-3
+    L.gemm(dY, W, M, N, K, b_mn=True, mode=L.EPI_GELU_BWD, out0=out, aux=gp, colsum=cs, impl=impl)
+    assert rel(out.float(), (dY.float() @ W.float()) * gp.float()) < 4e-3
     assert rel(cs, out.float().sum(0)) < 1e-4
 
 
