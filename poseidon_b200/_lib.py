@@ -1,7 +1,7 @@
 """ctypes binding of libscot_b200.so (the C ABI declared in include/scot_b200.h).
 
 There is deliberately no fallback: if the shared library is missing or a call fails, a RuntimeError is
-raised. The product path never routes through the oracle or any CPU implementation.
+raised. The product path never routes through any CPU implementation.
 """
 from __future__ import annotations
 
