@@ -293,7 +293,7 @@ struct FwdCfg {
   static constexpr size_t smem = (size_t)UPC * 3 * N * ROWB * 2 + (size_t)UPC * TABN * 4;
 };
 
-template <int WS, int HD>
+template <int WS, int HD, bool SHIFT>
 __global__ void __launch_bounds__(FwdCfg<WS, HD>::NWARP * 32)
 attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
                 const float* __restrict__ tab2, const float* __restrict__ alpha, WinGeom g, int total_units) {
@@ -364,11 +364,13 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
         for (int j = 0; j < 2; ++j) {
           const int n = kc * KC + nt * 8 + 2 * cq + j;
           const int co = bias_coloff<WS>(n);
-          const int cn = mask_code<WS>(wf, g.shift, n);
           float v0 = fmaf(s[nt][j], a2, utab[rb0 - co]);
           float v1 = fmaf(s[nt][2 + j], a2, utab[rb1 - co]);
-          if (cn != code0) v0 -= 200.0f * kLog2e;
-          if (cn != code1) v1 -= 200.0f * kLog2e;
+          if constexpr (SHIFT) {
+            const int cn = mask_code<WS>(wf, g.shift, n);
+            if (cn != code0) v0 -= 200.0f * kLog2e;
+            if (cn != code1) v1 -= 200.0f * kLog2e;
+          }
           s[nt][j] = v0;
           s[nt][2 + j] = v1;
           cm0 = fmaxf(cm0, v0);
@@ -450,7 +452,7 @@ struct DqCfg {
                                  + (size_t)TABN * 4 + (size_t)NWARP * 16 * 4 /*inv norms*/;
 };
 
-template <int WS, int HD, int NWARP>
+template <int WS, int HD, int NWARP, bool SHIFT>
 __global__ void __launch_bounds__(NWARP * 32)
 attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf, const bf16* __restrict__ do_buf,
                    const float* __restrict__ lse, const float* __restrict__ tab2, const float* __restrict__ alpha,
@@ -562,11 +564,13 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
         for (int j = 0; j < 2; ++j) {
           const int n = kc * KC + nt * 8 + 2 * cq + j;
           const int co = bias_coloff<WS>(n);
-          const int cn = mask_code<WS>(wf, g.shift, n);
           float v0 = fmaf(s[nt][j], a2, stab[rb0 - co]);
           float v1 = fmaf(s[nt][2 + j], a2, stab[rb1 - co]);
-          if (cn != code0) v0 -= 200.0f * kLog2e;
-          if (cn != code1) v1 -= 200.0f * kLog2e;
+          if constexpr (SHIFT) {
+            const int cn = mask_code<WS>(wf, g.shift, n);
+            if (cn != code0) v0 -= 200.0f * kLog2e;
+            if (cn != code1) v1 -= 200.0f * kLog2e;
+          }
           const float p0 = exp2f(v0 - L0), p1 = exp2f(v1 - L1);
           ds[j] = p0 * (dp[nt][j] - D0);
           ds[2 + j] = p1 * (dp[nt][2 + j] - D1);
@@ -696,7 +700,7 @@ struct DkvCfg {
                                  + (size_t)TABN * 4 + (size_t)NWARP * 16 * 4;
 };
 
-template <int WS, int HD, int NWARP>
+template <int WS, int HD, int NWARP, bool SHIFT>
 __global__ void __launch_bounds__(NWARP * 32)
 attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf, const bf16* __restrict__ do_buf,
                     const float* __restrict__ lse, const float* __restrict__ tab2, const float* __restrict__ alpha,
@@ -810,12 +814,14 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
         for (int j = 0; j < 2; ++j) {
           const int m = qc * QC + nt * 8 + 2 * cq + j;  // query index (column)
           const int rb = bias_rowbase<WS>(m);
-          const int cm = mask_code<WS>(wf, g.shift, m);
           const float Lm = ulse[m], Dm = uD[m];
           float v0 = fmaf(st[nt][j], a2, stab[rb - co0]);
           float v1 = fmaf(st[nt][2 + j], a2, stab[rb - co1]);
-          if (cm != code0) v0 -= 200.0f * kLog2e;
-          if (cm != code1) v1 -= 200.0f * kLog2e;
+          if constexpr (SHIFT) {
+            const int cm = mask_code<WS>(wf, g.shift, m);
+            if (cm != code0) v0 -= 200.0f * kLog2e;
+            if (cm != code1) v1 -= 200.0f * kLog2e;
+          }
           p[j] = exp2f(v0 - Lm);
           p[2 + j] = exp2f(v1 - Lm);
           ds[j] = p[j] * (dpt[nt][j] - Dm) * al;
@@ -897,12 +903,13 @@ template <int WS, int HD>
 int launch_fwd(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, WinGeom g, int total_windows,
                cudaStream_t st) {
   using Cfg = FwdCfg<WS, HD>;
-  auto kern = attn_fwd_kernel<WS, HD>;
   static bool done = false;
   if (!done) {
-    SCOT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem));
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<WS, HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem));
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<WS, HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem));
     done = true;
   }
+  auto kern = g.shift > 0 ? attn_fwd_kernel<WS, HD, true> : attn_fwd_kernel<WS, HD, false>;
   const int units = total_windows * g.heads;
   const int grid = ceil_div(units, Cfg::UPC);
   kern<<<grid, Cfg::NWARP * 32, Cfg::smem, st>>>((const bf16*)qkv, (bf16*)out, lse, tab2, alpha, g, units);
@@ -916,14 +923,16 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
                float* g_vbias, WinGeom g, int total_windows, cudaStream_t st) {
   using C1 = DqCfg<WS, HD, NWARP>;
   using C2 = DkvCfg<WS, HD, NWARP>;
-  auto k1 = attn_bwd_dq_kernel<WS, HD, NWARP>;
-  auto k2 = attn_bwd_dkv_kernel<WS, HD, NWARP>;
   static bool done = false;
   if (!done) {
-    SCOT_CHECK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::smem));
-    SCOT_CHECK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::smem));
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<WS, HD, NWARP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::smem));
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<WS, HD, NWARP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::smem));
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<WS, HD, NWARP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::smem));
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<WS, HD, NWARP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::smem));
     done = true;
   }
+  auto k1 = g.shift > 0 ? attn_bwd_dq_kernel<WS, HD, NWARP, true> : attn_bwd_dq_kernel<WS, HD, NWARP, false>;
+  auto k2 = g.shift > 0 ? attn_bwd_dkv_kernel<WS, HD, NWARP, true> : attn_bwd_dkv_kernel<WS, HD, NWARP, false>;
   // dq kernel: ~200 KB of smem -> one CTA per SM, so size the grid to a single wave; fewer chunks also means
   // fewer bias-gradient dumps for the second-stage reduction
   const int iters = ceil_div(total_windows, C1::WPI);

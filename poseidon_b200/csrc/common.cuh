@@ -65,7 +65,8 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
   const float ax = fabsf(x) * 0.70710678118654752440f;           // |x|/sqrt(2)
   const float e2 = __expf(-0.5f * x * x);                         // exp(-x^2/2) = exp(-ax^2)
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float t;  // 1/(1 + p|x|/sqrt2): MUFU.RCP (1 ulp) is plenty for a result that is rounded to bf16
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

@@ -49,8 +49,6 @@ __device__ __forceinline__ float4 epi_load_aux(const EpiArgs& ep, long row, int 
   if constexpr (MODE == SCOT_EPI_GELU_BWD) {
     const uint2 h = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux) + row * ep.ldaux + col);
     return make_float4(__uint_as_float(h.x), __uint_as_float(h.y), 0.f, 0.f);
-  } else if constexpr (MODE == SCOT_EPI_RMW_F32) {
-    return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.out0) + row * ep.ld0 + col);
   } else if constexpr (MODE == SCOT_EPI_ADD_F32_BF16) {
     return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.aux) + row * ep.ldaux + col);
   } else {
@@ -93,10 +91,9 @@ __device__ __forceinline__ void epi_store(const EpiArgs& ep, long row, int col, 
     *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out0) + row * ep.ld0 + col) = o;
     const float2 r01 = unpack_bf16x2(o.x), r23 = unpack_bf16x2(o.y);  // column sums of what was stored
     csum.x += r01.x; csum.y += r01.y; csum.z += r23.x; csum.w += r23.y;
-  } else if constexpr (MODE == SCOT_EPI_RMW_F32) {
-    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out0) + row * ep.ld0 + col);
-    *p = make_float4(aux.x + v.x, aux.y + v.y, aux.z + v.z, aux.w + v.w);
-  } else if constexpr (MODE == SCOT_EPI_ATOMIC_F32) {
+  } else if constexpr (MODE == SCOT_EPI_RMW_F32 || MODE == SCOT_EPI_ATOMIC_F32) {
+    // "+=" on a fp32 tensor: the add is performed by the L2 (fire-and-forget red.add), so the SM never waits for
+    // the old value. RMW_F32 (one writer per element) is deterministic, ATOMIC_F32 (split reduction) is not.
     float* p = reinterpret_cast<float*>(ep.out0) + row * ep.ld0 + col;
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
@@ -126,7 +123,7 @@ struct TileCfg {
 };
 
 template <int BN, int AMN, int BMN, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, (BN <= 64 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                int kblocks_total, int kblocks_per_split, int tiles_m, int tiles_n, int total_tiles, int num_stages,
                EpiArgs ep) {
@@ -241,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int VPR = BN / 4;              // float4 per tile row
     constexpr int RPP = EPI_THREADS / VPR;   // rows per pass
     constexpr int NPASS = (BM + RPP - 1) / RPP;
-    constexpr bool kHasAux = (MODE == SCOT_EPI_GELU_BWD || MODE == SCOT_EPI_RMW_F32 || MODE == SCOT_EPI_ADD_F32_BF16);
+    constexpr bool kHasAux = (MODE == SCOT_EPI_GELU_BWD || MODE == SCOT_EPI_ADD_F32_BF16);
     constexpr int NCHUNK = BN / 32;          // 32-column TMEM chunks; warps 2-5 take the even ones, 6-9 the odd ones
     const int cv = et % VPR;
     const int r0 = et / VPR;
@@ -431,8 +428,11 @@ int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, in
   const int total_tiles = tiles_m * tiles_n * splits;
 
   // smem: barriers + operand ring + dedicated fp32 staging tile (the ring keeps running during the epilogue)
+  // BN <= 64: two CTAs per SM (two independent epilogue pipelines hide each other's latencies)
+  constexpr int kCtasPerSm = BN <= 64 ? 2 : 1;
   const size_t fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + (size_t)Cfg::kStagingBytes;
-  int stages = (int)((227 * 1024 - fixed) / Cfg::kStageBytes);
+  const size_t budget = (size_t)(227 * 1024) / kCtasPerSm - (kCtasPerSm > 1 ? 1024 : 0);
+  int stages = (int)((budget - fixed) / Cfg::kStageBytes);
   if (stages > 6) stages = 6;
   SCOT_REQUIRE(stages >= 2, "gemm: tile too large for shared memory");
   const size_t smem = fixed + (size_t)stages * Cfg::kStageBytes;
@@ -442,7 +442,8 @@ int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, in
     SCOT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
+  const int max_ctas = g_num_sms * kCtasPerSm;
+  const int grid = total_tiles < max_ctas ? total_tiles : max_ctas;
   kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, M, N, kblocks, kps, tiles_m, tiles_n, total_tiles, stages, ep);
   SCOT_LAUNCH_CHECK();
   return 0;
@@ -451,6 +452,10 @@ int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, in
 template <int AMN, int BMN, int MODE>
 int dispatch_bn(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
                 cudaStream_t stream) {
+  // epilogue-bound modes (two bf16 streams / transcendental math): 128 x 64 tiles, two resident CTAs per SM
+  if constexpr (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_GELU_BWD) {
+    if (N % 64 == 0 || N > 64) return launch_tc<64, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+  }
   if constexpr (BMN == 0) {
     if (N % 128 == 0) return launch_tc<128, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
     if (N % 96 == 0) return launch_tc<96, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);

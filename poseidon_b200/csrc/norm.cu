@@ -89,8 +89,7 @@ __global__ void __launch_bounds__(256) cln_fwd_kernel(ClnFwdArgs p) {
     const int c0 = cv * 4;
     float zh[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
     if (p.zhat != nullptr) {
-      // the saved normalised value is the bf16-rounded one; use the same rounded value below so that the
-      // backward pass differentiates exactly the function the forward pass evaluated
+      // saved for the backward pass in bf16 (the forward output below uses the unrounded fp32 value)
       uint2 o = make_uint2(pack_bf16x2(zh[0], zh[1]), pack_bf16x2(zh[2], zh[3]));
       *reinterpret_cast<uint2*>(p.zhat + r_out * p.C + c0) = o;
     }
@@ -169,62 +168,83 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
 #pragma unroll
   for (int i = 0; i < V; ++i) acc_a[i] = acc_c[i] = acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int rr = warp * RPW + sub; rr < p.rows_per_block; rr += nwarps * RPW) {
-    const long r_out = row_begin + rr;  // rows_per_block is a multiple of RPW so sub-warps stay converged
-    float4 dy[V], zh[V];
-    float s1 = 0.f, s2 = 0.f;
+  // R rows per (sub-)warp are processed together so that several independent global loads are in flight
+  constexpr int R = (V <= 3) ? 4 : (V <= 6 ? 2 : 1);
+  const int row_stride = nwarps * RPW;
+  for (int rr0 = warp * RPW + sub; rr0 < p.rows_per_block; rr0 += row_stride * R) {
+    float4 dy[R][V], zh[R][V];
+    float rs[R];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int cv = sl + i * LPR;
-      if (cv < nvec) {
-        dy[i] = *reinterpret_cast<const float4*>(p.dy + r_out * p.C + cv * 4);
-        const uint2 zr = *reinterpret_cast<const uint2*>(p.zhat + r_out * p.C + cv * 4);
-        const float2 z01 = unpack_bf16x2(zr.x), z23 = unpack_bf16x2(zr.y);
-        zh[i] = make_float4(z01.x, z01.y, z23.x, z23.y);
-        acc_a[i].x += dy[i].x * zh[i].x; acc_a[i].y += dy[i].y * zh[i].y;
-        acc_a[i].z += dy[i].z * zh[i].z; acc_a[i].w += dy[i].w * zh[i].w;
-        acc_c[i].x += dy[i].x; acc_c[i].y += dy[i].y; acc_c[i].z += dy[i].z; acc_c[i].w += dy[i].w;
-        // dzhat = dy * scale
-        dy[i].x *= sc[i].x; dy[i].y *= sc[i].y; dy[i].z *= sc[i].z; dy[i].w *= sc[i].w;
-        s1 += (dy[i].x + dy[i].y) + (dy[i].z + dy[i].w);
-        s2 += (dy[i].x * zh[i].x + dy[i].y * zh[i].y) + (dy[i].z * zh[i].z + dy[i].w * zh[i].w);
+    for (int k = 0; k < R; ++k) {
+      const int rr = rr0 + k * row_stride;
+      const long r_out = row_begin + rr;
+      rs[k] = (rr < p.rows_per_block) ? p.rstd[r_out] : 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int cv = sl + i * LPR;
+        if (cv < nvec && rr < p.rows_per_block) {
+          dy[k][i] = *reinterpret_cast<const float4*>(p.dy + r_out * p.C + cv * 4);
+          const uint2 zr = *reinterpret_cast<const uint2*>(p.zhat + r_out * p.C + cv * 4);
+          const float2 z01 = unpack_bf16x2(zr.x), z23 = unpack_bf16x2(zr.y);
+          zh[k][i] = make_float4(z01.x, z01.y, z23.x, z23.y);
+        } else {
+          dy[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          zh[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) {
-      s1 += __shfl_xor_sync(mask, s1, o);
-      s2 += __shfl_xor_sync(mask, s2, o);
-    }
-    const float m1 = s1 / (float)p.C, m2 = s2 / (float)p.C;
-    const float rstd = p.rstd[r_out];
-    long r_in = r_out;
-    if (p.perm_res > 0) {
-      // inverse of unmerge_row
-      const int w2 = 2 * p.perm_res;
-      const int x = (int)(r_out % w2);
-      const long tt = r_out / w2;
-      const int y = (int)(tt % w2);
-      const long b = tt / w2;
-      r_in = (((b * p.perm_res + (y >> 1)) * p.perm_res + (x >> 1)) << 2) + ((y & 1) << 1) + (x & 1);
-    }
+    for (int k = 0; k < R; ++k) {
+      const int rr = rr0 + k * row_stride;  // rows beyond the block contribute zeros and are not stored
+      const long r_out = row_begin + rr;
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int cv = sl + i * LPR;
-      if (cv < nvec) {
-        float4 dz;
-        dz.x = (dy[i].x - m1 - zh[i].x * m2) * rstd;
-        dz.y = (dy[i].y - m1 - zh[i].y * m2) * rstd;
-        dz.z = (dy[i].z - m1 - zh[i].z * m2) * rstd;
-        dz.w = (dy[i].w - m1 - zh[i].w * m2) * rstd;
-        if (p.dz_is_f32) {
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dz) + r_in * p.C + cv * 4) = dz;
-        } else {
-          const uint2 o = make_uint2(pack_bf16x2(dz.x, dz.y), pack_bf16x2(dz.z, dz.w));
-          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.dz) + r_in * p.C + cv * 4) = o;
-          const float2 a = unpack_bf16x2(o.x), b = unpack_bf16x2(o.y);
-          dz = make_float4(a.x, a.y, b.x, b.y);
+      for (int i = 0; i < V; ++i) {
+        acc_a[i].x += dy[k][i].x * zh[k][i].x; acc_a[i].y += dy[k][i].y * zh[k][i].y;
+        acc_a[i].z += dy[k][i].z * zh[k][i].z; acc_a[i].w += dy[k][i].w * zh[k][i].w;
+        acc_c[i].x += dy[k][i].x; acc_c[i].y += dy[k][i].y; acc_c[i].z += dy[k][i].z; acc_c[i].w += dy[k][i].w;
+        // dzhat = dy * scale
+        dy[k][i].x *= sc[i].x; dy[k][i].y *= sc[i].y; dy[k][i].z *= sc[i].z; dy[k][i].w *= sc[i].w;
+        s1 += (dy[k][i].x + dy[k][i].y) + (dy[k][i].z + dy[k][i].w);
+        s2 += (dy[k][i].x * zh[k][i].x + dy[k][i].y * zh[k][i].y) + (dy[k][i].z * zh[k][i].z + dy[k][i].w * zh[k][i].w);
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(mask, s1, o);
+        s2 += __shfl_xor_sync(mask, s2, o);
+      }
+      if (rr >= p.rows_per_block) continue;
+      const float m1 = s1 / (float)p.C, m2 = s2 / (float)p.C;
+      const float rstd = rs[k];
+      long r_in = r_out;
+      if (p.perm_res > 0) {
+        // inverse of unmerge_row
+        const int w2 = 2 * p.perm_res;
+        const int x = (int)(r_out % w2);
+        const long tt = r_out / w2;
+        const int y = (int)(tt % w2);
+        const long b = tt / w2;
+        r_in = (((b * p.perm_res + (y >> 1)) * p.perm_res + (x >> 1)) << 2) + ((y & 1) << 1) + (x & 1);
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int cv = sl + i * LPR;
+        if (cv < nvec) {
+          float4 dz;
+          dz.x = (dy[k][i].x - m1 - zh[k][i].x * m2) * rstd;
+          dz.y = (dy[k][i].y - m1 - zh[k][i].y * m2) * rstd;
+          dz.z = (dy[k][i].z - m1 - zh[k][i].z * m2) * rstd;
+          dz.w = (dy[k][i].w - m1 - zh[k][i].w * m2) * rstd;
+          if (p.dz_is_f32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dz) + r_in * p.C + cv * 4) = dz;
+          } else {
+            const uint2 o = make_uint2(pack_bf16x2(dz.x, dz.y), pack_bf16x2(dz.z, dz.w));
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.dz) + r_in * p.C + cv * 4) = o;
+            const float2 a = unpack_bf16x2(o.x), b = unpack_bf16x2(o.y);
+            dz = make_float4(a.x, a.y, b.x, b.y);
+          }
+          acc_b[i].x += dz.x; acc_b[i].y += dz.y; acc_b[i].z += dz.z; acc_b[i].w += dz.w;
         }
-        acc_b[i].x += dz.x; acc_b[i].y += dz.y; acc_b[i].z += dz.z; acc_b[i].w += dz.w;
       }
     }
   }
