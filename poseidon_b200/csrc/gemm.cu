@@ -143,6 +143,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_mn = tiles_m * tiles_n;
+  // every CTA owns a contiguous range of tiles (m fastest): it streams down one column block of the output, so the
+  // B tile (weights) stays hot and per-column epilogue state (bias-gradient sums) is flushed at most twice
+  const int tiles_per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = min(total_tiles, t_begin + tiles_per_cta);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -167,7 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int it = 0;  // running k-block counter over all my tiles (ring position)
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_begin; t < t_end; ++t) {
         const int split = t / tiles_mn, rem = t - split * tiles_mn;
         const int m0 = (rem % tiles_m) * BM, n0 = (rem / tiles_m) * BN;  // m fastest: a CTA stays in one column block
         const int kb_begin = split * kblocks_per_split;
@@ -200,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, AMN, BMN);
       int it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      for (int t = t_begin; t < t_end; ++t, ++lt) {
         const int split = t / tiles_mn;
         const int kb_begin = split * kblocks_per_split;
         const int nkb = min(kb_begin + kblocks_per_split, kblocks_total) - kb_begin;
@@ -245,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool active = r0 < RPP;
     float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
     int lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+    for (int t = t_begin; t < t_end; ++t, ++lt) {
       const int split = t / tiles_mn, rem = t - split * tiles_mn;
       const int m0 = (rem % tiles_m) * BM, n0 = (rem / tiles_m) * BN;
       const int col = n0 + cv * 4;
@@ -309,8 +314,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if constexpr (MODE == SCOT_EPI_GELU_BWD) {
           // column sums (bias gradient): flush when the next tile of this CTA is in a different column block
-          const int tn = t + gridDim.x;
-          const bool last_of_col = (tn >= total_tiles) || ((tn % tiles_mn) / tiles_m) != (rem / tiles_m);
+          const int tn = t + 1;
+          const bool last_of_col = (tn >= t_end) || ((tn % tiles_mn) / tiles_m) != (rem / tiles_m);
           if (last_of_col && ep.colsum != nullptr) {
             atomicAdd(ep.colsum + col + 0, csum.x);
             atomicAdd(ep.colsum + col + 1, csum.y);

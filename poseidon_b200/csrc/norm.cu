@@ -327,7 +327,10 @@ int scot_cln_bwd_launch(const float* dy, const void* zhat, const float* rstd, co
   SCOT_REQUIRE(C % 4 == 0 && rows > 0, "cln_bwd: bad shape");
   SCOT_REQUIRE((aw == nullptr) == (g_aw == nullptr) && (g_aw == nullptr) == (g_cw == nullptr), "cln_bwd: aw/g_aw/g_cw mismatch");
   SCOT_REQUIRE(aw == nullptr || time != nullptr, "cln_bwd: conditioned norm needs time");
+  // rows per block: large enough that the per-block parameter-gradient atomics (5 per column) stay rare, small
+  // enough to fill the machine
   int rpb = rows_per_sample < 64 ? rows_per_sample : 64;
+  while (rpb < 256 && rows_per_sample % (rpb * 2) == 0 && rows / (rpb * 2) >= 296) rpb *= 2;
   SCOT_REQUIRE(rows_per_sample % rpb == 0 && rows % rpb == 0 && rpb % 4 == 0, "cln_bwd: rows_per_sample=%d unsupported",
                rows_per_sample);
   ClnBwdArgs a{dy, (const bf16*)zhat, rstd, time, aw, ab, dz, dz_is_f32, g_aw, g_ab, g_cw, g_cb, g_bias_prev, rows, C,
