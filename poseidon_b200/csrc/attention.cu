@@ -342,7 +342,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
     const int m0 = mt * 16 + gq, m1 = m0 + 8;
     const int rb0 = bias_rowbase<WS>(m0), rb1 = bias_rowbase<WS>(m1);
     const int wf = win_flags(g, bw);
-    const int code0 = mask_code<WS>(wf, g.shift, m0), code1 = mask_code<WS>(wf, g.shift, m1);
+    const int code0 = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, m0), code1 = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, m1);
 
     uint32_t qa[HD / 16][4];
     load_a_frags<HD>(qa, uq + mt * 16 * ROWB, lane);
@@ -367,7 +367,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
           float v0 = fmaf(s[nt][j], a2, utab[rb0 - co]);
           float v1 = fmaf(s[nt][2 + j], a2, utab[rb1 - co]);
           if constexpr (SHIFT) {
-            const int cn = mask_code<WS>(wf, g.shift, n);
+            const int cn = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, n);
             if (cn != code0) v0 -= 200.0f * kLog2e;
             if (cn != code1) v1 -= 200.0f * kLog2e;
           }
@@ -534,7 +534,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
     const int unit = bw * g.heads + h;
     const float L0 = lse[(long)unit * N + m0], L1 = lse[(long)unit * N + m1];
     const int wf = win_flags(g, bw);
-    const int code0 = mask_code<WS>(wf, g.shift, m0), code1 = mask_code<WS>(wf, g.shift, m1);
+    const int code0 = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, m0), code1 = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, m1);
     const bf16* uk = sk + wsub * N * ROWB;
     const bf16* uv = sv + wsub * N * ROWB;
 
@@ -567,7 +567,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
           float v0 = fmaf(s[nt][j], a2, stab[rb0 - co]);
           float v1 = fmaf(s[nt][2 + j], a2, stab[rb1 - co]);
           if constexpr (SHIFT) {
-            const int cn = mask_code<WS>(wf, g.shift, n);
+            const int cn = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, n);
             if (cn != code0) v0 -= 200.0f * kLog2e;
             if (cn != code1) v1 -= 200.0f * kLog2e;
           }
@@ -782,7 +782,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
     if (!active) continue;
 
     const int wf = win_flags(g, bw);
-    const int code0 = mask_code<WS>(wf, g.shift, n0), code1 = mask_code<WS>(wf, g.shift, n1);
+    const int code0 = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, n0), code1 = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, n1);
     const bf16* uq = sq + wsub * N * ROWB;
     const bf16* udo = sdo + wsub * N * ROWB;
     const float* ulse = slse + wsub * N;
@@ -818,7 +818,7 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
           float v0 = fmaf(st[nt][j], a2, stab[rb - co0]);
           float v1 = fmaf(st[nt][2 + j], a2, stab[rb - co1]);
           if constexpr (SHIFT) {
-            const int cm = mask_code<WS>(wf, g.shift, m);
+            const int cm = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, m);
             if (cm != code0) v0 -= 200.0f * kLog2e;
             if (cm != code1) v1 -= 200.0f * kLog2e;
           }
