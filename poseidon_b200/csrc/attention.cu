@@ -297,6 +297,8 @@ template <int WS, int HD, bool SHIFT>
 __global__ void __launch_bounds__(FwdCfg<WS, HD>::NWARP * 32)
 attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse,
                 const float* __restrict__ tab2, const float* __restrict__ alpha, WinGeom g, int total_units) {
+  pdl_launch_dependents();
+  pdl_wait();
   using Cfg = FwdCfg<WS, HD>;
   constexpr int N = Cfg::N, ROWB = Cfg::ROWB, KC = Cfg::KC, NT = KC / 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -458,6 +460,8 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
                    const float* __restrict__ lse, const float* __restrict__ tab2, const float* __restrict__ alpha,
                    bf16* __restrict__ dqkv, float* __restrict__ dbias_partial, float* __restrict__ dalpha,
                    float* __restrict__ g_qbias, WinGeom g, int total_windows, int windows_per_chunk) {
+  pdl_launch_dependents();
+  pdl_wait();
   using Cfg = DqCfg<WS, HD, NWARP>;
   constexpr int N = Cfg::N, ROWB = Cfg::ROWB, KC = Cfg::KC, NT = KC / 8, MT = Cfg::MT, WPI = Cfg::WPI;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -644,6 +648,8 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
 template <int WS, int NWARP>
 __global__ void __launch_bounds__(256)
 attn_bias_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dtab, int heads, int chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int N = WS * WS, MT = N / 16;
   constexpr int RG = (MT / NWARP) > 1 ? (MT / NWARP) : 1;
   constexpr int KC = N < 64 ? N : 64, NT = KC / 8;
@@ -706,6 +712,8 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
                     const float* __restrict__ lse, const float* __restrict__ tab2, const float* __restrict__ alpha,
                     bf16* __restrict__ dqkv, float* __restrict__ g_vbias, WinGeom g, int total_windows,
                     int windows_per_chunk) {
+  pdl_launch_dependents();
+  pdl_wait();
   using Cfg = DkvCfg<WS, HD, NWARP>;
   constexpr int N = Cfg::N, ROWB = Cfg::ROWB, QC = Cfg::QC, NT = QC / 8, MT = Cfg::MT, WPI = Cfg::WPI;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -912,7 +920,8 @@ int launch_fwd(const void* qkv, void* out, float* lse, const float* tab2, const 
   auto kern = g.shift > 0 ? attn_fwd_kernel<WS, HD, true> : attn_fwd_kernel<WS, HD, false>;
   const int units = total_windows * g.heads;
   const int grid = ceil_div(units, Cfg::UPC);
-  kern<<<grid, Cfg::NWARP * 32, Cfg::smem, st>>>((const bf16*)qkv, (bf16*)out, lse, tab2, alpha, g, units);
+  SCOT_CHECK_CUDA(scot_launch_pdl(kern, dim3(grid), dim3(Cfg::NWARP * 32), Cfg::smem, st, (const bf16*)qkv, (bf16*)out, lse, tab2,
+                                  alpha, g, units));
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -950,15 +959,16 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
   const int wpc2 = ceil_div(iters, chunks2) * C2::WPI;
   chunks2 = ceil_div(total_windows, wpc2);
   dim3 grid1(g.heads, C1::RG, chunks);
-  k1<<<grid1, NWARP * 32, C1::smem, st>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, tab2, alpha, (bf16*)dqkv,
-                                           partial, dalpha, g_qbias, g, total_windows, wpc);
+  SCOT_CHECK_CUDA(scot_launch_pdl(k1, grid1, dim3(NWARP * 32), C1::smem, st, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
+                                  tab2, alpha, (bf16*)dqkv, partial, dalpha, g_qbias, g, total_windows, wpc));
   SCOT_LAUNCH_CHECK();
   dim3 grid2(g.heads, C2::KG, chunks2);
-  k2<<<grid2, NWARP * 32, C2::smem, st>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, tab2, alpha, (bf16*)dqkv,
-                                           g_vbias, g, total_windows, wpc2);
+  SCOT_CHECK_CUDA(scot_launch_pdl(k2, grid2, dim3(NWARP * 32), C2::smem, st, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
+                                  tab2, alpha, (bf16*)dqkv, g_vbias, g, total_windows, wpc2));
   SCOT_LAUNCH_CHECK();
   const int red_y = WS == 16 ? 64 : (WS == 8 ? 4 : 1);
-  attn_bias_reduce_kernel<WS, NWARP><<<dim3(g.heads, red_y), 256, 0, st>>>(partial, dtab, g.heads, chunks);
+  SCOT_CHECK_CUDA(scot_launch_pdl(attn_bias_reduce_kernel<WS, NWARP>, dim3(g.heads, red_y), dim3(256), 0, st, (const float*)partial,
+                                  dtab, g.heads, chunks));
   SCOT_LAUNCH_CHECK();
   return 0;
 }

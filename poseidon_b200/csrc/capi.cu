@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "internal.h"
@@ -17,6 +18,14 @@ void scot_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void scot_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool scot_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SCOT_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 extern "C" {
 

@@ -42,6 +42,34 @@ void scot_count_launch();
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the hot kernels are launched with programmaticStreamSerialization so
+// that the launch + block scheduling (+ for the GEMM its barrier/TMEM setup) of kernel N+1 overlaps the
+// tail of kernel N. Each such kernel calls pdl_launch_dependents() first and pdl_wait() before it touches
+// global memory; ~1400 mostly 10-20 us kernels per training step make the launch gaps worth hiding.
+// SCOT_PDL=0 in the environment disables the attribute (plain stream order).
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+bool scot_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t scot_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = scot_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
 // generic device helpers

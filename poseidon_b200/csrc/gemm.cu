@@ -140,6 +140,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* tiles = smem + 1024;
   float* stage = reinterpret_cast<float*>(tiles + (size_t)num_stages * Cfg::kStageBytes);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_mn = tiles_m * tiles_n;
@@ -167,6 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -449,7 +451,8 @@ int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, in
   }
   const int max_ctas = g_num_sms * kCtasPerSm;
   const int grid = total_tiles < max_ctas ? total_tiles : max_ctas;
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, M, N, kblocks, kps, tiles_m, tiles_n, total_tiles, stages, ep);
+  SCOT_CHECK_CUDA(scot_launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, M, N, kblocks, kps, tiles_m,
+                                  tiles_n, total_tiles, stages, ep));
   SCOT_LAUNCH_CHECK();
   return 0;
 }

@@ -44,6 +44,8 @@ __device__ __forceinline__ long unmerge_row(long r_in, int res) {
 
 template <int LPR, int V>
 __global__ void __launch_bounds__(256) cln_fwd_kernel(ClnFwdArgs p) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int RPW = 32 / LPR;  // rows per warp
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, sl = lane % LPR;
@@ -138,6 +140,8 @@ struct ClnBwdArgs {
 
 template <int LPR, int V>
 __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];  // [3][C]
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -280,14 +284,14 @@ int launch_fwd(const ClnFwdArgs& a, cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
   const int warps = 8;
   const long blocks = (a.rows + (long)warps * RPW - 1) / ((long)warps * RPW);
-  cln_fwd_kernel<LPR, V><<<(unsigned)blocks, warps * 32, 0, st>>>(a);
+  SCOT_CHECK_CUDA(scot_launch_pdl(cln_fwd_kernel<LPR, V>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, a));
   SCOT_LAUNCH_CHECK();
   return 0;
 }
 template <int LPR, int V>
 int launch_bwd(const ClnBwdArgs& a, cudaStream_t st) {
   const long blocks = a.rows / a.rows_per_block;
-  cln_bwd_kernel<LPR, V><<<(unsigned)blocks, 256, 3 * a.C * sizeof(float), st>>>(a);
+  SCOT_CHECK_CUDA(scot_launch_pdl(cln_bwd_kernel<LPR, V>, dim3((unsigned)blocks), dim3(256), 3 * a.C * sizeof(float), st, a));
   SCOT_LAUNCH_CHECK();
   return 0;
 }
