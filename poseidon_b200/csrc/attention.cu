@@ -384,14 +384,14 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
       cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1));
       cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
       const float nm0 = fmaxf(mx0, cm0), nm1 = fmaxf(mx1, cm1);
-      const float sc0 = exp2f(mx0 - nm0), sc1 = exp2f(mx1 - nm1);
+      const float sc0 = fast_exp2(mx0 - nm0), sc1 = fast_exp2(mx1 - nm1);
       mx0 = nm0; mx1 = nm1;
       float rs0 = 0.f, rs1 = 0.f;
       uint32_t pa[NT / 2][4];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const float p0 = exp2f(s[nt][0] - nm0), p1 = exp2f(s[nt][1] - nm0);
-        const float p2 = exp2f(s[nt][2] - nm1), p3 = exp2f(s[nt][3] - nm1);
+        const float p0 = fast_exp2(s[nt][0] - nm0), p1 = fast_exp2(s[nt][1] - nm0);
+        const float p2 = fast_exp2(s[nt][2] - nm1), p3 = fast_exp2(s[nt][3] - nm1);
         rs0 += p0 + p1;
         rs1 += p2 + p3;
         pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -575,7 +575,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
             if (cn != code0) v0 -= 200.0f * kLog2e;
             if (cn != code1) v1 -= 200.0f * kLog2e;
           }
-          const float p0 = exp2f(v0 - L0), p1 = exp2f(v1 - L1);
+          const float p0 = fast_exp2(v0 - L0), p1 = fast_exp2(v1 - L1);
           ds[j] = p0 * (dp[nt][j] - D0);
           ds[2 + j] = p1 * (dp[nt][2 + j] - D1);
           acc_alpha = fmaf(ds[j], s[nt][j], acc_alpha);
@@ -830,8 +830,8 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
             if (cm != code0) v0 -= 200.0f * kLog2e;
             if (cm != code1) v1 -= 200.0f * kLog2e;
           }
-          p[j] = exp2f(v0 - Lm);
-          p[2 + j] = exp2f(v1 - Lm);
+          p[j] = fast_exp2(v0 - Lm);
+          p[2 + j] = fast_exp2(v1 - Lm);
           ds[j] = p[j] * (dpt[nt][j] - Dm) * al;
           ds[2 + j] = p[2 + j] * (dpt[nt][2 + j] - Dm) * al;
         }

@@ -142,51 +142,49 @@ template <int LPR, int V>
 __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float red[];  // [3][C]
+  extern __shared__ float red[];  // [5][C]
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int sub = lane / LPR, sl = lane % LPR;
   const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
   const int nvec = p.C >> 2;
-  for (int i = threadIdx.x; i < 3 * p.C; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 5 * p.C; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const long row_begin = (long)blockIdx.x * p.rows_per_block;
-  const float t = p.time != nullptr ? p.time[row_begin / p.rows_per_sample] : 0.f;
 
-  float4 sc[V];
+  // scale = ab + aw * t(row): the block may span several samples, so t is looked up per row
+  float4 sab[V], saw[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int cv = sl + i * LPR;
+    sab[i] = saw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cv < nvec) {
-      sc[i] = *reinterpret_cast<const float4*>(p.ab + cv * 4);
-      if (p.aw != nullptr) {
-        const float4 aw = *reinterpret_cast<const float4*>(p.aw + cv * 4);
-        sc[i].x = fmaf(aw.x, t, sc[i].x); sc[i].y = fmaf(aw.y, t, sc[i].y);
-        sc[i].z = fmaf(aw.z, t, sc[i].z); sc[i].w = fmaf(aw.w, t, sc[i].w);
-      }
-    } else {
-      sc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      sab[i] = *reinterpret_cast<const float4*>(p.ab + cv * 4);
+      if (p.aw != nullptr) saw[i] = *reinterpret_cast<const float4*>(p.aw + cv * 4);
     }
   }
-  float4 acc_a[V], acc_c[V], acc_b[V];  // sum dy*zhat, sum dy, sum dz
+  // column sums: dy*zhat, dy, dz and (conditioned norm) the same two weighted by t
+  float4 acc_a[V], acc_c[V], acc_b[V], acc_at[V], acc_ct[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) acc_a[i] = acc_c[i] = acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < V; ++i) acc_a[i] = acc_c[i] = acc_b[i] = acc_at[i] = acc_ct[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // R rows per (sub-)warp are processed together so that several independent global loads are in flight
   constexpr int R = (V <= 3) ? 4 : (V <= 6 ? 2 : 1);
   const int row_stride = nwarps * RPW;
   for (int rr0 = warp * RPW + sub; rr0 < p.rows_per_block; rr0 += row_stride * R) {
     float4 dy[R][V], zh[R][V];
-    float rs[R];
+    float rs[R], tt[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const int rr = rr0 + k * row_stride;
       const long r_out = row_begin + rr;
-      rs[k] = (rr < p.rows_per_block) ? p.rstd[r_out] : 0.f;
+      const bool in = rr < p.rows_per_block && r_out < p.rows;
+      rs[k] = in ? p.rstd[r_out] : 0.f;
+      tt[k] = (in && p.time != nullptr) ? p.time[r_out / p.rows_per_sample] : 0.f;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int cv = sl + i * LPR;
-        if (cv < nvec && rr < p.rows_per_block) {
+        if (cv < nvec && in) {
           dy[k][i] = *reinterpret_cast<const float4*>(p.dy + r_out * p.C + cv * 4);
           const uint2 zr = *reinterpret_cast<const uint2*>(p.zhat + r_out * p.C + cv * 4);
           const float2 z01 = unpack_bf16x2(zr.x), z23 = unpack_bf16x2(zr.y);
@@ -204,11 +202,18 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        acc_a[i].x += dy[k][i].x * zh[k][i].x; acc_a[i].y += dy[k][i].y * zh[k][i].y;
-        acc_a[i].z += dy[k][i].z * zh[k][i].z; acc_a[i].w += dy[k][i].w * zh[k][i].w;
+        const float4 pz = make_float4(dy[k][i].x * zh[k][i].x, dy[k][i].y * zh[k][i].y, dy[k][i].z * zh[k][i].z,
+                                      dy[k][i].w * zh[k][i].w);
+        const float t = tt[k];
+        acc_a[i].x += pz.x; acc_a[i].y += pz.y; acc_a[i].z += pz.z; acc_a[i].w += pz.w;
         acc_c[i].x += dy[k][i].x; acc_c[i].y += dy[k][i].y; acc_c[i].z += dy[k][i].z; acc_c[i].w += dy[k][i].w;
-        // dzhat = dy * scale
-        dy[k][i].x *= sc[i].x; dy[k][i].y *= sc[i].y; dy[k][i].z *= sc[i].z; dy[k][i].w *= sc[i].w;
+        acc_at[i].x = fmaf(t, pz.x, acc_at[i].x); acc_at[i].y = fmaf(t, pz.y, acc_at[i].y);
+        acc_at[i].z = fmaf(t, pz.z, acc_at[i].z); acc_at[i].w = fmaf(t, pz.w, acc_at[i].w);
+        acc_ct[i].x = fmaf(t, dy[k][i].x, acc_ct[i].x); acc_ct[i].y = fmaf(t, dy[k][i].y, acc_ct[i].y);
+        acc_ct[i].z = fmaf(t, dy[k][i].z, acc_ct[i].z); acc_ct[i].w = fmaf(t, dy[k][i].w, acc_ct[i].w);
+        // dzhat = dy * scale(t)
+        dy[k][i].x *= fmaf(saw[i].x, t, sab[i].x); dy[k][i].y *= fmaf(saw[i].y, t, sab[i].y);
+        dy[k][i].z *= fmaf(saw[i].z, t, sab[i].z); dy[k][i].w *= fmaf(saw[i].w, t, sab[i].w);
         s1 += (dy[k][i].x + dy[k][i].y) + (dy[k][i].z + dy[k][i].w);
         s2 += (dy[k][i].x * zh[k][i].x + dy[k][i].y * zh[k][i].y) + (dy[k][i].z * zh[k][i].z + dy[k][i].w * zh[k][i].w);
       }
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
         s1 += __shfl_xor_sync(mask, s1, o);
         s2 += __shfl_xor_sync(mask, s2, o);
       }
-      if (rr >= p.rows_per_block) continue;
+      if (rr >= p.rows_per_block || r_out >= p.rows) continue;
       const float m1 = s1 / (float)p.C, m2 = s2 / (float)p.C;
       const float rstd = rs[k];
       long r_in = r_out;
@@ -258,24 +263,22 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
     const int cv = sl + i * LPR;
     if (cv < nvec) {
       const int c0 = cv * 4;
-      atomicAdd(&red[c0 + 0], acc_a[i].x); atomicAdd(&red[c0 + 1], acc_a[i].y);
-      atomicAdd(&red[c0 + 2], acc_a[i].z); atomicAdd(&red[c0 + 3], acc_a[i].w);
-      atomicAdd(&red[p.C + c0 + 0], acc_c[i].x); atomicAdd(&red[p.C + c0 + 1], acc_c[i].y);
-      atomicAdd(&red[p.C + c0 + 2], acc_c[i].z); atomicAdd(&red[p.C + c0 + 3], acc_c[i].w);
-      atomicAdd(&red[2 * p.C + c0 + 0], acc_b[i].x); atomicAdd(&red[2 * p.C + c0 + 1], acc_b[i].y);
-      atomicAdd(&red[2 * p.C + c0 + 2], acc_b[i].z); atomicAdd(&red[2 * p.C + c0 + 3], acc_b[i].w);
+#define RED4(SLOT, ACC)                                                                               \
+  atomicAdd(&red[(SLOT) * p.C + c0 + 0], (ACC).x); atomicAdd(&red[(SLOT) * p.C + c0 + 1], (ACC).y); \
+  atomicAdd(&red[(SLOT) * p.C + c0 + 2], (ACC).z); atomicAdd(&red[(SLOT) * p.C + c0 + 3], (ACC).w);
+      RED4(0, acc_a[i]) RED4(1, acc_c[i]) RED4(2, acc_b[i]) RED4(3, acc_at[i]) RED4(4, acc_ct[i])
+#undef RED4
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const float sa = red[c], scs = red[p.C + c], sb = red[2 * p.C + c];
-    atomicAdd(p.g_ab + c, sa);
-    atomicAdd(p.g_cb + c, scs);
+    atomicAdd(p.g_ab + c, red[c]);
+    atomicAdd(p.g_cb + c, red[p.C + c]);
+    if (p.g_bias_prev != nullptr) atomicAdd(p.g_bias_prev + c, red[2 * p.C + c]);
     if (p.g_aw != nullptr) {
-      atomicAdd(p.g_aw + c, sa * t);
-      atomicAdd(p.g_cw + c, scs * t);
+      atomicAdd(p.g_aw + c, red[3 * p.C + c]);
+      atomicAdd(p.g_cw + c, red[4 * p.C + c]);
     }
-    if (p.g_bias_prev != nullptr) atomicAdd(p.g_bias_prev + c, sb);
   }
 }
 
@@ -290,8 +293,8 @@ int launch_fwd(const ClnFwdArgs& a, cudaStream_t st) {
 }
 template <int LPR, int V>
 int launch_bwd(const ClnBwdArgs& a, cudaStream_t st) {
-  const long blocks = a.rows / a.rows_per_block;
-  SCOT_CHECK_CUDA(scot_launch_pdl(cln_bwd_kernel<LPR, V>, dim3((unsigned)blocks), dim3(256), 3 * a.C * sizeof(float), st, a));
+  const long blocks = (a.rows + a.rows_per_block - 1) / a.rows_per_block;
+  SCOT_CHECK_CUDA(scot_launch_pdl(cln_bwd_kernel<LPR, V>, dim3((unsigned)blocks), dim3(256), 5 * a.C * sizeof(float), st, a));
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -331,13 +334,12 @@ int scot_cln_bwd_launch(const float* dy, const void* zhat, const float* rstd, co
   SCOT_REQUIRE(C % 4 == 0 && rows > 0, "cln_bwd: bad shape");
   SCOT_REQUIRE((aw == nullptr) == (g_aw == nullptr) && (g_aw == nullptr) == (g_cw == nullptr), "cln_bwd: aw/g_aw/g_cw mismatch");
   SCOT_REQUIRE(aw == nullptr || time != nullptr, "cln_bwd: conditioned norm needs time");
-  // rows per block: large enough that the per-block parameter-gradient atomics (5 per column) stay rare, small
-  // enough to fill the machine
-  int rpb = rows_per_sample < 64 ? rows_per_sample : 64;
-  while (rpb < 256 && rows_per_sample % (rpb * 2) == 0 && rows / (rpb * 2) >= 296) rpb *= 2;
-  SCOT_REQUIRE(rows_per_sample % rpb == 0 && rows % rpb == 0 && rpb % 4 == 0, "cln_bwd: rows_per_sample=%d unsupported",
-               rows_per_sample);
+  // a block sweeps a contiguous range of rows (it may span samples): about two blocks per SM keep the per-block
+  // reduction + 5 atomics per column rare while every warp still has several rows in flight
+  long rpb = (rows + 295) / 296;
+  rpb = (rpb + 31) / 32 * 32;
+  if (rpb < 32) rpb = 32;
   ClnBwdArgs a{dy, (const bf16*)zhat, rstd, time, aw, ab, dz, dz_is_f32, g_aw, g_ab, g_cw, g_cb, g_bias_prev, rows, C,
-               rows_per_sample, rpb, perm_res};
+               rows_per_sample, (int)rpb, perm_res};
   CLN_DISPATCH(launch_bwd, a);
 }
