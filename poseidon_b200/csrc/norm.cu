@@ -6,6 +6,8 @@
 // Call sites fused here: ScOTLayer res-post-norm adds (model.py:570,574), ScOTEmbeddings.norm (:352),
 // ScOTPatchMerging.norm (:710), ScOTPatchUnmerging permute+norm (:748-759), ConvNeXtBlock.norm (:208).
 // HBM-bound: one (sub-)warp per token row, 128-bit loads, shuffle reductions, row kept in registers.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -142,14 +144,12 @@ template <int LPR, int V>
 __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float red[];  // [5][C]
+  extern __shared__ float red[];  // [warps][5][C]
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int sub = lane / LPR, sl = lane % LPR;
   const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
   const int nvec = p.C >> 2;
-  for (int i = threadIdx.x; i < 5 * p.C; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
   const long row_begin = (long)blockIdx.x * p.rows_per_block;
 
   // scale = ab + aw * t(row): the block may span several samples, so t is looked up per row
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
   for (int i = 0; i < V; ++i) acc_a[i] = acc_c[i] = acc_b[i] = acc_at[i] = acc_ct[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // R rows per (sub-)warp are processed together so that several independent global loads are in flight
-  constexpr int R = (V <= 3) ? 4 : (V <= 6 ? 2 : 1);
+  constexpr int R = (V == 1) ? 8 : (V <= 3) ? 4 : (V <= 6 ? 2 : 1);
   const int row_stride = nwarps * RPW;
   for (int rr0 = warp * RPW + sub; rr0 < p.rows_per_block; rr0 += row_stride * R) {
     float4 dy[R][V], zh[R][V];
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
       const long r_out = row_begin + rr;
       const bool in = rr < p.rows_per_block && r_out < p.rows;
       rs[k] = in ? p.rstd[r_out] : 0.f;
-      tt[k] = (in && p.time != nullptr) ? p.time[r_out / p.rows_per_sample] : 0.f;
+      tt[k] = (in && p.time != nullptr) ? p.time[(int)r_out / p.rows_per_sample] : 0.f;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int cv = sl + i * LPR;
@@ -257,28 +257,39 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
       }
     }
   }
-  // block reduction (smem atomics; a handful per thread) then one global atomic per column per array
+  // block reduction without atomics: fold the row sub-groups of a warp with shuffles, park one partial per warp in
+  // smem ([warp][5][C]), then every thread sums a few columns over the warps and issues the global atomics
+#define FOLD4(ACC)                                                              \
+  _Pragma("unroll") for (int o = LPR; o < 32; o <<= 1) {                        \
+    (ACC).x += __shfl_xor_sync(0xffffffffu, (ACC).x, o);                        \
+    (ACC).y += __shfl_xor_sync(0xffffffffu, (ACC).y, o);                        \
+    (ACC).z += __shfl_xor_sync(0xffffffffu, (ACC).z, o);                        \
+    (ACC).w += __shfl_xor_sync(0xffffffffu, (ACC).w, o);                        \
+  }
+  float* wred = red + (size_t)warp * 5 * p.C;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
+    if (LPR < 32) {
+      FOLD4(acc_a[i]) FOLD4(acc_c[i]) FOLD4(acc_b[i]) FOLD4(acc_at[i]) FOLD4(acc_ct[i])
+    }
     const int cv = sl + i * LPR;
-    if (cv < nvec) {
+    if (cv < nvec && sub == 0) {
       const int c0 = cv * 4;
-#define RED4(SLOT, ACC)                                                                               \
-  atomicAdd(&red[(SLOT) * p.C + c0 + 0], (ACC).x); atomicAdd(&red[(SLOT) * p.C + c0 + 1], (ACC).y); \
-  atomicAdd(&red[(SLOT) * p.C + c0 + 2], (ACC).z); atomicAdd(&red[(SLOT) * p.C + c0 + 3], (ACC).w);
-      RED4(0, acc_a[i]) RED4(1, acc_c[i]) RED4(2, acc_b[i]) RED4(3, acc_at[i]) RED4(4, acc_ct[i])
-#undef RED4
+      *reinterpret_cast<float4*>(wred + 0 * p.C + c0) = acc_a[i];
+      *reinterpret_cast<float4*>(wred + 1 * p.C + c0) = acc_c[i];
+      *reinterpret_cast<float4*>(wred + 2 * p.C + c0) = acc_b[i];
+      *reinterpret_cast<float4*>(wred + 3 * p.C + c0) = acc_at[i];
+      *reinterpret_cast<float4*>(wred + 4 * p.C + c0) = acc_ct[i];
     }
   }
+#undef FOLD4
   __syncthreads();
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    atomicAdd(p.g_ab + c, red[c]);
-    atomicAdd(p.g_cb + c, red[p.C + c]);
-    if (p.g_bias_prev != nullptr) atomicAdd(p.g_bias_prev + c, red[2 * p.C + c]);
-    if (p.g_aw != nullptr) {
-      atomicAdd(p.g_aw + c, red[3 * p.C + c]);
-      atomicAdd(p.g_cw + c, red[4 * p.C + c]);
-    }
+  for (int k = threadIdx.x; k < 5 * p.C; k += blockDim.x) {
+    float v = 0.f;
+    for (int w = 0; w < nwarps; ++w) v += red[(size_t)w * 5 * p.C + k];
+    const int slot = k / p.C, c = k - slot * p.C;
+    float* dst = slot == 0 ? p.g_ab : slot == 1 ? p.g_cb : slot == 2 ? p.g_bias_prev : slot == 3 ? p.g_aw : p.g_cw;
+    if (dst != nullptr) atomicAdd(dst + c, v);
   }
 }
 
@@ -294,7 +305,13 @@ int launch_fwd(const ClnFwdArgs& a, cudaStream_t st) {
 template <int LPR, int V>
 int launch_bwd(const ClnBwdArgs& a, cudaStream_t st) {
   const long blocks = (a.rows + a.rows_per_block - 1) / a.rows_per_block;
-  SCOT_CHECK_CUDA(scot_launch_pdl(cln_bwd_kernel<LPR, V>, dim3((unsigned)blocks), dim3(256), 5 * a.C * sizeof(float), st, a));
+  const size_t smem = (size_t)8 * 5 * a.C * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(cln_bwd_kernel<LPR, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 5 * 4 * LPR * V * 4));
+    attr_done = true;
+  }
+  SCOT_CHECK_CUDA(scot_launch_pdl(cln_bwd_kernel<LPR, V>, dim3((unsigned)blocks), dim3(256), smem, st, a));
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -336,9 +353,20 @@ int scot_cln_bwd_launch(const float* dy, const void* zhat, const float* rstd, co
   SCOT_REQUIRE(aw == nullptr || time != nullptr, "cln_bwd: conditioned norm needs time");
   // a block sweeps a contiguous range of rows (it may span samples): about two blocks per SM keep the per-block
   // reduction + 5 atomics per column rare while every warp still has several rows in flight
-  long rpb = (rows + 295) / 296;
-  rpb = (rpb + 31) / 32 * 32;
+  // rows per block: enough blocks to fill the machine several times over (every warp keeps R rows in flight), but at
+  // least 32 rows so that the per-block column reduction + 5 atomics per column stay a small fraction
+  long rpb = rows / (8 * 148);
+  rpb = rpb / 32 * 32;
   if (rpb < 32) rpb = 32;
+  if (rpb > 128) rpb = 128;
+  {
+    static long override_rpb = -1;  // tuning knob: SCOT_CLN_RPB=<rows per block>
+    if (override_rpb < 0) {
+      const char* e = getenv("SCOT_CLN_RPB");
+      override_rpb = e ? atol(e) : 0;
+    }
+    if (override_rpb > 0) rpb = override_rpb;
+  }
   ClnBwdArgs a{dy, (const bf16*)zhat, rstd, time, aw, ab, dz, dz_is_f32, g_aw, g_ab, g_cw, g_cb, g_bias_prev, rows, C,
                rows_per_sample, (int)rpb, perm_res};
   CLN_DISPATCH(launch_bwd, a);
