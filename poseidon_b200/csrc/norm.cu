@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
   for (int i = 0; i < V; ++i) acc_a[i] = acc_c[i] = acc_b[i] = acc_at[i] = acc_ct[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // R rows per (sub-)warp are processed together so that several independent global loads are in flight
-  constexpr int R = (V == 1) ? 8 : (V <= 3) ? 4 : (V <= 6 ? 2 : 1);
+  constexpr int R = (V <= 3) ? 4 : (V <= 6 ? 2 : 1);
   const int row_stride = nwarps * RPW;
   for (int rr0 = warp * RPW + sub; rr0 < p.rows_per_block; rr0 += row_stride * R) {
     float4 dy[R][V], zh[R][V];
@@ -355,10 +355,7 @@ int scot_cln_bwd_launch(const float* dy, const void* zhat, const float* rstd, co
   // reduction + 5 atomics per column rare while every warp still has several rows in flight
   // rows per block: enough blocks to fill the machine several times over (every warp keeps R rows in flight), but at
   // least 32 rows so that the per-block column reduction + 5 atomics per column stay a small fraction
-  long rpb = rows / (8 * 148);
-  rpb = rpb / 32 * 32;
-  if (rpb < 32) rpb = 32;
-  if (rpb > 128) rpb = 128;
+  long rpb = rows >= 16384 ? 128 : 32;  // measured on B200 (scripts/cln_bwd_sweep.py): larger blocks only add latency
   {
     static long override_rpb = -1;  // tuning knob: SCOT_CLN_RPB=<rows per block>
     if (override_rpb < 0) {
