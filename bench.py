@@ -305,6 +305,37 @@ def main():
             torch.distributed.destroy_process_group()
         return
 
+    # ---- dominant kernel (roofline): the tcgen05 GEMM family is ~45 % of the step (profiles/); its most expensive
+    # instance is the stage-0 MLP up-projection with the fused GELU epilogue: [B*1024, C] x [4C, C]^T -> gelu'(h), gelu(h).
+    # HBM bound (K = C = 96: 65 FLOP/B): algorithmic bytes = A + W + bias + two bf16 outputs. Timed alone with CUDA events on
+    # the launching stream; three buffer sets (3 x 113 MB > 126 MB L2) are cycled so that no launch finds its data in L2.
+    from poseidon_b200 import _lib as L
+    C0 = cfg["embed_dim"]
+    Mk, Nk, Kk = B * (cfg["image_size"] // cfg["patch_size"]) ** 2, 4 * C0, C0
+    sets = []
+    for _ in range(3):
+        sets.append((torch.randn(Mk, Kk, device=dev).bfloat16(), torch.randn(Nk, Kk, device=dev).bfloat16(),
+                     torch.randn(Nk, device=dev), torch.empty(Mk, Nk, device=dev, dtype=torch.bfloat16),
+                     torch.empty(Mk, Nk, device=dev, dtype=torch.bfloat16)))
+
+    def kern(i):
+        a_, b_, bias_, o0, o1 = sets[i % 3]
+        L.gemm(a_, b_, Mk, Nk, Kk, mode=L.EPI_GELU, bias=bias_, out0=o0, out1=o1)
+
+    for i in range(6):
+        kern(i)
+    torch.cuda.synchronize(dev)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nk = 30
+    k0.record()
+    for i in range(nk):
+        kern(i)
+    k1.record()
+    torch.cuda.synchronize(dev)
+    kern_us = k0.elapsed_time(k1) / nk * 1e3
+    kern_bytes = (Mk * Kk + Nk * Kk) * 2 + Nk * 4 + 2 * Mk * Nk * 2
+    del sets
+
     total_samples = B * world
     sps = total_samples / (ms * 1e-3)
     f_step = 3.0 * (B * flops_forward_per_sample(cfg) + flops_cpb_per_step(cfg))  # per GPU
@@ -312,8 +343,10 @@ def main():
     if os.path.exists(peaks_path):
         pk = json.load(open(peaks_path))
         peak_tf, peak_src = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0))), "MEASURED_PEAKS.json bf16_tflops_sustained"
+        peak_hbm, hbm_src = float(pk.get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+        peak_hbm, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved_tf = f_step / (ms * 1e-3) / 1e12
     rec = {
         "metric": "samples/sec (fwd+bwd)", "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -327,9 +360,15 @@ def main():
                 "ms_per_step": e2e_ms},
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
+        # dominant kernel: gemm_tc_kernel<64, K-major, K-major, GELU> at the stage-0 MLP shape, HBM bound
+        "roofline": {"bound": "hbm", "achieved": kern_bytes / (kern_us * 1e-6) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                     "frac": kern_bytes / (kern_us * 1e-6) / 1e9 / peak_hbm,
+                     # dram__bytes_read+write of this launch from profiles/r01_ncu_full_summary.md (L2 keeps part of the output)
+                     "traffic": 55.6e6, "kernel": f"gemm_tc_kernel<64,K,K,GELU> M={Mk} N={Nk} K={Kk}", "us_per_launch": kern_us,
+                     "algorithmic_bytes": kern_bytes, "peak_source": hbm_src},
         # whole-step tensor roofline (the BASELINE metric): algorithmic fwd+bwd FLOPs / step time vs measured cuBLAS peak
-        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": None, "scope": "whole step (all kernels)", "peak_source": peak_src},
+        "step_tensor_roofline": {"achieved_tflops": achieved_tf, "peak_tflops": peak_tf, "frac": achieved_tf / peak_tf,
+                                 "peak_source": peak_src},
     }
     if not args.no_cpu_baseline:
         try:

@@ -464,6 +464,12 @@ int dispatch_bn(const void* A, long lda, const void* B, long ldb, int M, int N, 
   if constexpr (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_GELU_BWD) {
     if (N % 64 == 0 || N > 64) return launch_tc<64, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
   }
+  // small problems (deep stages: a few thousand tokens): 128-wide tiles would leave most SMs idle and make every CTA
+  // stream K/64 x 32 KB through one SM's L2 port; the 64-wide tile doubles the CTA count (two per SM)
+  if constexpr (MODE != SCOT_EPI_ATOMIC_F32) {
+    if (ceil_div(M, BM) * ceil_div(N, 128) < g_num_sms && N > 64)
+      return launch_tc<64, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+  }
   if constexpr (BMN == 0) {
     if (N % 128 == 0) return launch_tc<128, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
     if (N % 96 == 0) return launch_tc<96, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
