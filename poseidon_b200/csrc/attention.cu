@@ -52,6 +52,15 @@ __device__ __forceinline__ int mask_code(int flags, int shift, int n) {
   const int wm = (flags & 2) && (n % WS >= WS - shift);
   return hm | (wm << 1);
 }
+// WS == 16, shift == 8: an 8-column mma tile lies inside one half of one window row, so "masked or not" is uniform
+// per (row half, column tile): returns the additive mask term (2 x -100, HF:465-468, in log2 units) for the
+// column tile n8 = n / 8 against a row with region bits (row_h, row_w).
+__device__ __forceinline__ float mask_term16(int wf, int row_h, int row_w, int n8) {
+  const int col_h = (wf & 1) && ((n8 >> 1) >= 8);
+  const int col_w = (wf & 2) && (n8 & 1);
+  return (row_h != col_h || row_w != col_w) ? -200.0f * kLog2e : 0.0f;
+}
+
 template <int WS>
 __device__ __forceinline__ int bias_rowbase(int m) {
   return (m / WS) * (2 * WS - 1) + (m % WS) + (WS - 1) * (2 * WS - 1) + (WS - 1);
@@ -368,7 +377,10 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
           const int co = bias_coloff<WS>(n);
           float v0 = fmaf(s[nt][j], a2, utab[rb0 - co]);
           float v1 = fmaf(s[nt][2 + j], a2, utab[rb1 - co]);
-          if constexpr (SHIFT) {
+          if constexpr (SHIFT && WS == 16) {
+            v0 += mask_term16(wf, code0 & 1, code0 >> 1, kc * (KC / 8) + nt);
+            v1 += mask_term16(wf, code1 & 1, code1 >> 1, kc * (KC / 8) + nt);
+          } else if constexpr (SHIFT) {
             const int cn = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, n);
             if (cn != code0) v0 -= 200.0f * kLog2e;
             if (cn != code1) v1 -= 200.0f * kLog2e;
@@ -570,7 +582,10 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
           const int co = bias_coloff<WS>(n);
           float v0 = fmaf(s[nt][j], a2, stab[rb0 - co]);
           float v1 = fmaf(s[nt][2 + j], a2, stab[rb1 - co]);
-          if constexpr (SHIFT) {
+          if constexpr (SHIFT && WS == 16) {
+            v0 += mask_term16(wf, code0 & 1, code0 >> 1, kc * (KC / 8) + nt);
+            v1 += mask_term16(wf, code1 & 1, code1 >> 1, kc * (KC / 8) + nt);
+          } else if constexpr (SHIFT) {
             const int cn = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, n);
             if (cn != code0) v0 -= 200.0f * kLog2e;
             if (cn != code1) v1 -= 200.0f * kLog2e;
@@ -825,7 +840,10 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
           const float Lm = ulse[m], Dm = uD[m];
           float v0 = fmaf(st[nt][j], a2, stab[rb - co0]);
           float v1 = fmaf(st[nt][2 + j], a2, stab[rb - co1]);
-          if constexpr (SHIFT) {
+          if constexpr (SHIFT && WS == 16) {
+            v0 += mask_term16(wf, code0 & 1, code0 >> 1, qc * (QC / 8) + nt);
+            v1 += mask_term16(wf, code1 & 1, code1 >> 1, qc * (QC / 8) + nt);
+          } else if constexpr (SHIFT) {
             const int cm = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, m);
             if (cm != code0) v0 -= 200.0f * kLog2e;
             if (cm != code1) v1 -= 200.0f * kLog2e;
