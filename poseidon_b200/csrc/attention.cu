@@ -52,13 +52,22 @@ __device__ __forceinline__ int mask_code(int flags, int shift, int n) {
   const int wm = (flags & 2) && (n % WS >= WS - shift);
   return hm | (wm << 1);
 }
-// WS == 16, shift == 8: an 8-column mma tile lies inside one half of one window row, so "masked or not" is uniform
-// per (row half, column tile): returns the additive mask term (2 x -100, HF:465-468, in log2 units) for the
-// column tile n8 = n / 8 against a row with region bits (row_h, row_w).
-__device__ __forceinline__ float mask_term16(int wf, int row_h, int row_w, int n8) {
-  const int col_h = (wf & 1) && ((n8 >> 1) >= 8);
-  const int col_w = (wf & 2) && (n8 & 1);
-  return (row_h != col_h || row_w != col_w) ? -200.0f * kLog2e : 0.0f;
+// WS == 16, shift == 8, 64-column chunks: an 8-column mma tile lies inside one half of one window row, so "masked or
+// not" is uniform per (row half, column tile) and, within a chunk, depends only on the parity of the tile index:
+// four additive terms (2 x -100, HF:465-468, in log2 units) per chunk replace a per-element region compare.
+struct MaskTerms16 {
+  float r0_even, r0_odd, r1_even, r1_odd;
+};
+__device__ __forceinline__ MaskTerms16 mask_terms16(int wf, int code0, int code1, int chunk) {
+  const int col_h = (wf & 1) && (chunk >= 2);  // columns chunk*64.. : window row index = chunk*4 + tile/2 >= 8
+  const int lastc = (wf >> 1) & 1;             // odd tiles are the right half (q >= 8) of a window row
+  const float neg = -200.0f * kLog2e;
+  MaskTerms16 t;
+  t.r0_even = ((code0 & 1) != col_h || (code0 >> 1) != 0) ? neg : 0.f;
+  t.r0_odd = ((code0 & 1) != col_h || (code0 >> 1) != lastc) ? neg : 0.f;
+  t.r1_even = ((code1 & 1) != col_h || (code1 >> 1) != 0) ? neg : 0.f;
+  t.r1_odd = ((code1 & 1) != col_h || (code1 >> 1) != lastc) ? neg : 0.f;
+  return t;
 }
 
 template <int WS>
@@ -368,6 +377,8 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
       mma_a_bT<HD, NT>(s, qa, uk, kc * KC, lane);
+      MaskTerms16 mterm = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (SHIFT && WS == 16) mterm = mask_terms16(wf, code0, code1, kc);
       float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
@@ -378,8 +389,8 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
           float v0 = fmaf(s[nt][j], a2, utab[rb0 - co]);
           float v1 = fmaf(s[nt][2 + j], a2, utab[rb1 - co]);
           if constexpr (SHIFT && WS == 16) {
-            v0 += mask_term16(wf, code0 & 1, code0 >> 1, kc * (KC / 8) + nt);
-            v1 += mask_term16(wf, code1 & 1, code1 >> 1, kc * (KC / 8) + nt);
+            v0 += (nt & 1) ? mterm.r0_odd : mterm.r0_even;
+            v1 += (nt & 1) ? mterm.r1_odd : mterm.r1_even;
           } else if constexpr (SHIFT) {
             const int cn = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, n);
             if (cn != code0) v0 -= 200.0f * kLog2e;
@@ -571,6 +582,8 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
       }
       mma_a_bT<HD, NT>(s, qa, uk, kc * KC, lane);
       mma_a_bT<HD, NT>(dp, da, uv, kc * KC, lane);
+      MaskTerms16 mterm = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (SHIFT && WS == 16) mterm = mask_terms16(wf, code0, code1, kc);
       uint32_t dsa[NT / 2][4];
       float* accp = myacc + (kc * NT) * 128 + lane;
 #pragma unroll
@@ -583,8 +596,8 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
           float v0 = fmaf(s[nt][j], a2, stab[rb0 - co]);
           float v1 = fmaf(s[nt][2 + j], a2, stab[rb1 - co]);
           if constexpr (SHIFT && WS == 16) {
-            v0 += mask_term16(wf, code0 & 1, code0 >> 1, kc * (KC / 8) + nt);
-            v1 += mask_term16(wf, code1 & 1, code1 >> 1, kc * (KC / 8) + nt);
+            v0 += (nt & 1) ? mterm.r0_odd : mterm.r0_even;
+            v1 += (nt & 1) ? mterm.r1_odd : mterm.r1_even;
           } else if constexpr (SHIFT) {
             const int cn = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, n);
             if (cn != code0) v0 -= 200.0f * kLog2e;
@@ -722,7 +735,7 @@ struct DkvCfg {
 };
 
 template <int WS, int HD, int NWARP, bool SHIFT>
-__global__ void __launch_bounds__(NWARP * 32)
+__global__ void __launch_bounds__(NWARP * 32, (HD <= 32 ? 2 : 1))
 attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf, const bf16* __restrict__ do_buf,
                     const float* __restrict__ lse, const float* __restrict__ tab2, const float* __restrict__ alpha,
                     bf16* __restrict__ dqkv, float* __restrict__ g_vbias, WinGeom g, int total_windows,
@@ -829,6 +842,8 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
       }
       mma_a_bT<HD, NT>(st, ka, uq, qc * QC, lane);    // S^T tile: rows = keys, cols = queries
       mma_a_bT<HD, NT>(dpt, va, udo, qc * QC, lane);  // dP^T tile
+      MaskTerms16 mterm = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (SHIFT && WS == 16) mterm = mask_terms16(wf, code0, code1, qc);
       uint32_t pta[NT / 2][4], dsta[NT / 2][4];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
@@ -841,8 +856,8 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
           float v0 = fmaf(st[nt][j], a2, stab[rb - co0]);
           float v1 = fmaf(st[nt][2 + j], a2, stab[rb - co1]);
           if constexpr (SHIFT && WS == 16) {
-            v0 += mask_term16(wf, code0 & 1, code0 >> 1, qc * (QC / 8) + nt);
-            v1 += mask_term16(wf, code1 & 1, code1 >> 1, qc * (QC / 8) + nt);
+            v0 += (nt & 1) ? mterm.r0_odd : mterm.r0_even;
+            v1 += (nt & 1) ? mterm.r1_odd : mterm.r1_even;
           } else if constexpr (SHIFT) {
             const int cm = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, m);
             if (cm != code0) v0 -= 200.0f * kLog2e;
