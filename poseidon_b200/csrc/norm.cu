@@ -305,13 +305,16 @@ int launch_fwd(const ClnFwdArgs& a, cudaStream_t st) {
 template <int LPR, int V>
 int launch_bwd(const ClnBwdArgs& a, cudaStream_t st) {
   const long blocks = (a.rows + a.rows_per_block - 1) / a.rows_per_block;
-  const size_t smem = (size_t)8 * 5 * a.C * sizeof(float);
+  const int warps = a.C > 768 ? 4 : 8;  // [warps][5][C] floats of smem must fit 227 KB (C = 1536: Poseidon-L stage 3)
+  const size_t smem = (size_t)warps * 5 * a.C * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
-    SCOT_CHECK_CUDA(cudaFuncSetAttribute(cln_bwd_kernel<LPR, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 5 * 4 * LPR * V * 4));
+    constexpr int kMaxC = 4 * LPR * V;
+    constexpr int kMaxSmem = (kMaxC > 768 ? 4 : 8) * 5 * kMaxC * 4;
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(cln_bwd_kernel<LPR, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_done = true;
   }
-  SCOT_CHECK_CUDA(scot_launch_pdl(cln_bwd_kernel<LPR, V>, dim3((unsigned)blocks), dim3(256), smem, st, a));
+  SCOT_CHECK_CUDA(scot_launch_pdl(cln_bwd_kernel<LPR, V>, dim3((unsigned)blocks), dim3(warps * 32), smem, st, a));
   SCOT_LAUNCH_CHECK();
   return 0;
 }
