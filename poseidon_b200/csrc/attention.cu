@@ -650,10 +650,15 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
     }
   }
   __syncthreads();
-  // dump bias-gradient accumulators: [chunk][head][rg][warp][16*N]
+  // add this CTA's bias-gradient accumulators into the per-head buffer [head][rg][warp][16*N] (L2 red.add, 16 B
+  // per op): the sum over window chunks happens in the L2 instead of a [chunks][...] dump + second-stage reduction
   {
-    const long base = (((long)chunk * g.heads + h) * Cfg::RG + rg) * NWARP * Cfg::ACC_PER_WARP;
-    for (int i = tid; i < NWARP * Cfg::ACC_PER_WARP; i += nthreads) dbias_partial[base + i] = sacc[i];
+    float* dst = dbias_partial + ((long)h * Cfg::RG + rg) * NWARP * Cfg::ACC_PER_WARP;
+    for (int i = tid * 4; i < NWARP * Cfg::ACC_PER_WARP; i += nthreads * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(sacc + i);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
+    }
   }
   acc_alpha = warp_sum(acc_alpha);
   if (lane == 0) atomicAdd(dalpha + h, acc_alpha);
@@ -675,7 +680,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
 // positions onto the (2ws-1)^2 table through the relative position index (HF:512-523).
 template <int WS, int NWARP>
 __global__ void __launch_bounds__(256)
-attn_bias_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dtab, int heads, int chunks) {
+attn_bias_reduce_kernel(float* __restrict__ partial, float* __restrict__ dtab, int heads, int chunks) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int N = WS * WS, MT = N / 16;
@@ -690,15 +695,9 @@ attn_bias_reduce_kernel(const float* __restrict__ partial, float* __restrict__ d
   const int per_cta = (PER_HEAD + gridDim.y - 1) / gridDim.y;
   const int p0 = blockIdx.y * per_cta, p1 = min(PER_HEAD, p0 + per_cta);
   for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-    const float* src = partial + (long)h * PER_HEAD + p;
-    const long cs = (long)heads * PER_HEAD;
-    int c = 0;
-    for (; c + 4 <= chunks; c += 4) {
-      v0 += src[(c + 0) * cs]; v1 += src[(c + 1) * cs]; v2 += src[(c + 2) * cs]; v3 += src[(c + 3) * cs];
-    }
-    for (; c < chunks; ++c) v0 += src[c * cs];
-    const float v = (v0 + v1) + (v2 + v3);
+    float* src = partial + (long)h * PER_HEAD + p;
+    const float v = *src;
+    *src = 0.f;  // leave the accumulation buffer clean for the next layer
     // decode slot -> (row m, col n)
     const int rgw = p / (16 * N);      // rg * NWARP + warp
     const int slot = p - rgw * 16 * N;
@@ -983,7 +982,7 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
   if (chunks < 1) chunks = 1;
   int wpc = ceil_div(iters, chunks) * C1::WPI;
   chunks = ceil_div(total_windows, wpc);
-  const size_t need = (size_t)chunks * g.heads * C1::RG * NWARP * C1::ACC_PER_WARP * sizeof(float);
+  const size_t need = (size_t)g.heads * C1::RG * NWARP * C1::ACC_PER_WARP * sizeof(float);
   SCOT_REQUIRE(need <= partial_bytes, "attention backward: bias partial buffer too small (%zu > %zu)", need, partial_bytes);
   // dk/dv kernel: ~66 KB of smem -> three CTAs per SM
   int chunks2 = (3 * num_sms()) / (g.heads * C2::KG);
@@ -999,9 +998,9 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
   SCOT_CHECK_CUDA(scot_launch_pdl(k2, grid2, dim3(NWARP * 32), C2::smem, st, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
                                   tab2, alpha, (bf16*)dqkv, g_vbias, g, total_windows, wpc2));
   SCOT_LAUNCH_CHECK();
-  const int red_y = WS == 16 ? 64 : (WS == 8 ? 4 : 1);
-  SCOT_CHECK_CUDA(scot_launch_pdl(attn_bias_reduce_kernel<WS, NWARP>, dim3(g.heads, red_y), dim3(256), 0, st, (const float*)partial,
-                                  dtab, g.heads, chunks));
+  const int red_y = WS == 16 ? 32 : (WS == 8 ? 4 : 1);
+  SCOT_CHECK_CUDA(scot_launch_pdl(attn_bias_reduce_kernel<WS, NWARP>, dim3(g.heads, red_y), dim3(256), 0, st, partial, dtab, g.heads,
+                                  chunks));
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -1009,14 +1008,13 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
 }  // namespace
 
 size_t scot_attn_bwd_partial_bytes(int ws, int heads, int total_windows) {
-  // upper bound used by the planner: chunks <= 2*SMs/(heads*RG) + 1
+  // [head][N x N] fp32 accumulation buffer (RG * NWARP * 16 * N = N * N positions per head, or 8 x 16 x N when several
+  // windows share a CTA). Must be ZERO on entry to scot_attn_bwd; it is zero again on return.
+  (void)total_windows;
   const int N = ws * ws;
-  const int nwarp = 8;
   const int mt = N / 16;
-  const int rg = mt / nwarp > 1 ? mt / nwarp : 1;
-  int chunks = ceil_div(2 * 160, heads * rg) + 1;
-  if (chunks > total_windows) chunks = total_windows;
-  return (size_t)chunks * heads * rg * nwarp * 16 * N * sizeof(float);
+  const int per_head = (mt >= 8 ? mt : 8) * 16 * N;
+  return (size_t)heads * per_head * sizeof(float);
 }
 
 int scot_cpb_fwd_launch(const ScotCpbTable* tab, const float* params, void* arena, cudaStream_t st) {

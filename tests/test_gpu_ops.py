@@ -238,7 +238,7 @@ def test_window_attention_forward_backward(L, case):
     dqkv = torch.zeros(M, 3 * C, device=dev, dtype=torch.bfloat16)
     import ctypes
     pbytes = L.load().scot_attn_bwd_partial_bytes(ws, heads, nwin)
-    partial = torch.empty(pbytes // 4, device=dev)
+    partial = torch.zeros(pbytes // 4, device=dev)  # accumulation buffer: zero on entry, zero again on return
     dtab, dalpha = cpb.dtab, cpb.dalpha
     gq = torch.zeros(C, device=dev)
     gv = torch.zeros(C, device=dev)
@@ -248,6 +248,7 @@ def test_window_attention_forward_backward(L, case):
     assert rel(dqkv[:, :C].float(), g_ref[:, :C]) < 3e-2, "dq"
     assert rel(dqkv[:, C:2 * C].float(), g_ref[:, C:2 * C]) < 3e-2, "dk"
     assert rel(gq, dqkv[:, :C].float().sum(0)) < 1e-3 and rel(gv, dqkv[:, 2 * C:].float().sum(0)) < 1e-3
+    assert float(partial.abs().max()) == 0.0
     # bias-table / logit-scale gradients through the two-stage reduction + cpb backward
     cpb.backward()
     g1, gb, g2, gls = cpb.grad(0, w1.shape), cpb.grad(1, b1.shape), cpb.grad(2, w2.shape), cpb.grad(3, (heads,))
