@@ -69,6 +69,20 @@ typedef struct ScotEpilogue {
 int scot_gemm_bf16(const void* A, long lda, int a_mn_major, const void* B, long ldb, int b_mn_major, int M, int N,
                    int K, const ScotEpilogue* epi, int impl, void* stream);
 
+/* weight gradients of up to 4 Linear layers in one launch: dW[n_out, n_in] (f32, ld_dw) += dY[tokens, n_out]^T X[tokens, n_in]
+ * (dY, X bf16). Replaces the four autograd wgrad GEMMs of a ScOTLayer (q/k/v, attention output, intermediate, output). */
+typedef struct ScotWgradProblem {
+  const void* dY;
+  long ld_dy;
+  const void* X;
+  long ld_x;
+  float* dW;
+  long ld_dw;
+  long tokens;
+  int n_out, n_in;
+} ScotWgradProblem;
+int scot_gemm_wgrad_group(const ScotWgradProblem* problems, int n, int impl, void* stream);
+
 
 /* ---- per-op entry points (used by the parity tests; the engine below calls the same launchers) ------
  * Layouts: activations are token-major [batch*res*res, C]; "f32"/"bf16" name the element type. */

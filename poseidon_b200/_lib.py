@@ -100,6 +100,11 @@ class ScotModelDesc(C.Structure):
     ]
 
 
+class ScotWgradProblem(C.Structure):
+    _fields_ = [("dY", C.c_void_p), ("ld_dy", C.c_long), ("X", C.c_void_p), ("ld_x", C.c_long), ("dW", C.c_void_p),
+                ("ld_dw", C.c_long), ("tokens", C.c_long), ("n_out", C.c_int), ("n_in", C.c_int)]
+
+
 class ScotCpbLayer(C.Structure):
     _fields_ = [("w1", C.c_int), ("b1", C.c_int), ("w2", C.c_int), ("ls", C.c_int), ("tab2", C.c_int), ("alpha", C.c_int),
                 ("dtab", C.c_int), ("dalpha", C.c_int), ("dpre", C.c_int), ("ws", C.c_short), ("heads", C.c_short)]
@@ -111,6 +116,8 @@ class ScotCpbTable(C.Structure):
 
 def _declare_engine(lib):
     vp, i, l, f = C.c_void_p, C.c_int, C.c_long, C.c_float
+    lib.scot_gemm_wgrad_group.argtypes = [C.POINTER(ScotWgradProblem), i, i, vp]
+    lib.scot_gemm_wgrad_group.restype = i
     lib.scot_cln_fwd.argtypes = [vp] * 11 + [l, i, i, i, f, vp]
     lib.scot_cln_fwd.restype = i
     lib.scot_cln_bwd.argtypes = [vp] * 7 + [i] + [vp] * 5 + [l, i, i, i, vp]
@@ -233,6 +240,15 @@ class CpbLayerBuffers:
     def backward(self):
         check(load().scot_cpb_bwd(C.byref(self.table), ptr(self.params), ptr(self.grads), ptr(self.arena), cur_stream()),
               "scot_cpb_bwd")
+
+
+def wgrad_group(problems, impl=GEMM_TCGEN05):
+    """problems: list of (dY [tokens, n_out] bf16, X [tokens, n_in] bf16, dW [n_out, n_in] f32); dW += dY^T X, one launch"""
+    arr = (ScotWgradProblem * len(problems))()
+    for k, (dY, X, dW) in enumerate(problems):
+        arr[k] = ScotWgradProblem(dY.data_ptr(), dY.stride(0), X.data_ptr(), X.stride(0), dW.data_ptr(), dW.stride(0),
+                                  dY.shape[0], dY.shape[1], X.shape[1])
+    check(load().scot_gemm_wgrad_group(arr, len(problems), impl, cur_stream()), "scot_gemm_wgrad_group")
 
 
 def attn_fwd(qkv, out, lse, tab2, alpha, batch, res, ws, shift, heads, hd):

@@ -38,6 +38,9 @@ int scot_gemm_bf16(const void* A, long lda, int a_mn_major, const void* B, long 
   return scot_gemm_launch(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, epi, impl, (cudaStream_t)stream);
 }
 
+int scot_gemm_wgrad_group(const ScotWgradProblem* problems, int n, int impl, void* stream) {
+  return scot_gemm_wgrad_group_launch(problems, n, impl, (cudaStream_t)stream);
+}
 int scot_cln_fwd(const float* z, const float* residual, const float* time, const float* aw, const float* ab,
                  const float* cw, const float* cb, float* x_out, void* xb_out, void* zhat, float* rstd, long rows, int C,
                  int rows_per_sample, int perm_res, float eps, void* stream) {

@@ -88,7 +88,7 @@ struct ScotEngine {
   size_t rec_bias, rec_D, rec_P, pred_copy, loss_sums;
   size_t z32, y32;                       // fp32 scratch [M0*C0] each
   // backward scratch
-  size_t dzb, dqkv, dh, dob, partial, dpre, dpred, dD16, dgrads_zero_begin, dgrads_zero_bytes;
+  size_t dzb, dzb2, dqkv, dh, dob, partial, dpre, dpred, dD16, dgrads_zero_begin, dgrads_zero_bytes;
   size_t partial_bytes;
   std::vector<size_t> gstage;            // fp32 [M_s, C_s]
   std::vector<ScotCpbTable> cpb_tables;  // relative-position-bias MLPs of all attention layers (<= 64 per table)
@@ -334,6 +334,7 @@ int build_plan(ScotEngine* e) {
     max_h = h2 > max_h ? h2 : max_h;
   }
   e->dzb = b.take(M0 * C0 * 2);
+  e->dzb2 = b.take(M0 * C0 * 2);
   e->dqkv = b.take(M0 * 3 * C0 * 2);
   e->dh = b.take(max_h * 2);
   e->dob = b.take(M0 * C0 * 2);
@@ -457,23 +458,23 @@ int block_fwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, in
   return 0;
 }
 
-// g: gradient wrt the block output on entry, wrt the block input on exit (fp32, in place)
+// g: gradient wrt the block output on entry, wrt the block input on exit (fp32, in place).
+// The four weight-gradient GEMMs are side branches of the chain: their operands stay alive until the end of the block
+// (separate dz buffers for the two norms), so they are issued as ONE grouped launch after the data-gradient chain.
 int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, int shift, float* gr, const bf16* xb_in) {
   const ScotEngine* e = c.e;
   const long M = g.M, C = g.C, H = hidden_of(e, g.C);
   const int T = g.res * g.res;
   bf16* dzb = c.at<bf16>(e->dzb);
+  bf16* dzb2 = c.at<bf16>(e->dzb2);
   bf16* dh = c.at<bf16>(e->dh);
   // y = y1 + LN2(mlp(y1))
-  RC(norm_bwd(c, p.ln2, gr, c.at<bf16>(b.zhat2), c.at<float>(b.rstd2), dzb, 0, c.g(p.b2), M, (int)C, T, 0));
-  RC(gemm(c, dzb, C, 1, c.at<bf16>(b.g), H, 1, C, H, M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.w2), H));
-  RC(gemm(c, dzb, C, 0, c.w16(p.w2), H, 1, M, H, C, SCOT_EPI_GELU_BWD, nullptr, dh, H, nullptr, 0, c.at<bf16>(b.h), H,
+  RC(norm_bwd(c, p.ln2, gr, c.at<bf16>(b.zhat2), c.at<float>(b.rstd2), dzb2, 0, c.g(p.b2), M, (int)C, T, 0));
+  RC(gemm(c, dzb2, C, 0, c.w16(p.w2), H, 1, M, H, C, SCOT_EPI_GELU_BWD, nullptr, dh, H, nullptr, 0, c.at<bf16>(b.h), H,
           c.g(p.b1)));
-  RC(gemm(c, dh, H, 1, c.at<bf16>(b.y1b), C, 1, H, C, M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.w1), C));
   RC(gemm(c, dh, H, 0, c.w16(p.w1), C, 1, M, C, H, SCOT_EPI_RMW_F32, nullptr, gr, C));
   // y1 = x + LN1(attn(x))
   RC(norm_bwd(c, p.ln1, gr, c.at<bf16>(b.zhat1), c.at<float>(b.rstd1), dzb, 0, c.g(p.bo), M, (int)C, T, 0));
-  RC(gemm(c, dzb, C, 1, c.at<bf16>(b.o), C, 1, C, C, M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.wo), C));
   bf16* dob = c.at<bf16>(e->dob);
   RC(gemm(c, dzb, C, 0, c.w16(p.wo), C, 1, M, C, C, SCOT_EPI_BF16, nullptr, dob, C));
   bf16* dqkv = c.at<bf16>(e->dqkv);
@@ -481,8 +482,14 @@ int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, in
                           c.at<float>(b.alpha), dqkv, c.at<float>(e->partial), e->partial_bytes, c.at<float>(b.dtab),
                           c.at<float>(b.dalpha), c.g(p.bqkv), c.g(p.bqkv + 2 * C), e->batch, g.res, g.ws, shift, g.heads,
                           g.hd, c.st));
-  RC(gemm(c, dqkv, 3 * C, 1, xb_in, C, 1, 3 * C, C, M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.wqkv), C));
   RC(gemm(c, dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
+  const ScotWgradProblem wg[4] = {
+      {dzb2, C, c.at<bf16>(b.g), H, c.g(p.w2), H, M, (int)C, (int)H},         // output.dense
+      {dh, H, c.at<bf16>(b.y1b), C, c.g(p.w1), C, M, (int)H, (int)C},         // intermediate.dense
+      {dzb, C, c.at<bf16>(b.o), C, c.g(p.wo), C, M, (int)C, (int)C},          // attention.output.dense
+      {dqkv, 3 * C, xb_in, C, c.g(p.wqkv), C, M, (int)(3 * C), (int)C},       // query | key | value
+  };
+  RC(scot_gemm_wgrad_group_launch(wg, 4, c.impl, c.st));
   return 0;
 }
 
@@ -750,12 +757,14 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
       bf16* dzb = c.at<bf16>(e->dzb);
       bf16* dh = c.at<bf16>(e->dh);
       RC(scot_scale_add_bwd_launch(gr, c.at<bf16>(b.z2b), c.p(p.gamma), dzb, c.g(p.gamma), c.g(p.b2), g.M, g.C, c.st));
-      RC(gemm(c, dzb, g.C, 1, c.at<bf16>(b.g), 4L * g.C, 1, g.C, 4L * g.C, g.M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.w2),
-              4L * g.C));
       RC(gemm(c, dzb, g.C, 0, c.w16(p.w2), 4L * g.C, 1, g.M, 4L * g.C, g.C, SCOT_EPI_GELU_BWD, nullptr, dh, 4L * g.C, nullptr,
               0, c.at<bf16>(b.h), 4L * g.C, c.g(p.b1)));
-      RC(gemm(c, dh, 4L * g.C, 1, c.at<bf16>(b.nb), g.C, 1, 4L * g.C, g.C, g.M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(p.w1), g.C));
       RC(gemm(c, dh, 4L * g.C, 0, c.w16(p.w1), g.C, 1, g.M, g.C, 4L * g.C, SCOT_EPI_F32, nullptr, c.at<float>(e->z32), g.C));
+      const ScotWgradProblem wg[2] = {
+          {dzb, g.C, c.at<bf16>(b.g), 4L * g.C, c.g(p.w2), 4L * g.C, g.M, g.C, 4 * g.C},  // pwconv2
+          {dh, 4L * g.C, c.at<bf16>(b.nb), g.C, c.g(p.w1), g.C, g.M, 4 * g.C, g.C},        // pwconv1
+      };
+      RC(scot_gemm_wgrad_group_launch(wg, 2, c.impl, c.st));
       RC(norm_bwd(c, p.norm, c.at<float>(e->z32), c.at<bf16>(b.zhat), c.at<float>(b.rstd), c.at<float>(e->y32), 1,
                   c.g(p.bdw), g.M, g.C, g.res * g.res, 0));
       RC(scot_dwconv7_bwd_launch(blk_in, c.p(p.wdw), c.at<float>(e->y32), gr, gr, c.g(p.wdw), B, g.res, g.C, c.st));

@@ -20,7 +20,10 @@
 // These GEMMs have K = 96..3072 and are HBM/epilogue bound, so the design goal is to hide every fixed latency
 // (TMA round trip, TMEM allocation, store drain) behind the epilogue rather than to saturate the tensor pipe.
 // Tails in M, N and K are handled by TMA out-of-bounds zero fill + predicated stores.
+#include <cstring>
+
 #include "common.cuh"
+#include "internal.h"
 #include "scot_b200.h"
 
 namespace {
@@ -122,11 +125,43 @@ struct TileCfg {
   static constexpr int kStagingBytes = BM * kStagePitch * 4;
 };
 
+// One launch can carry up to kMaxGroup independent problems of the same tile configuration (the four weight-gradient
+// GEMMs of a transformer block are issued together): tiles are numbered across the problems.
+constexpr int kMaxGroup = 4;
+struct TileProblem {
+  CUtensorMap tmA, tmB;
+  int M, N, kblocks_total, kblocks_per_split, tiles_m, tiles_n, tile_begin, pad_;
+  EpiArgs ep;
+};
+struct GroupArgs {
+  int n, total_tiles;
+  TileProblem p[kMaxGroup];
+};
+
+struct TileCoord {
+  int pi, m0, n0, kb_begin, kb_end, col_block;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GroupArgs& ga, int t, int bn) {
+  TileCoord c;
+  c.pi = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxGroup; ++i)
+    if (i < ga.n && t >= ga.p[i].tile_begin) c.pi = i;
+  const TileProblem& P = ga.p[c.pi];
+  const int lt = t - P.tile_begin;
+  const int tiles_mn = P.tiles_m * P.tiles_n;
+  const int split = lt / tiles_mn, rem = lt - split * tiles_mn;
+  c.col_block = rem / P.tiles_m;  // m fastest: consecutive tiles walk down one column block of the output
+  c.m0 = (rem - c.col_block * P.tiles_m) * BM;
+  c.n0 = c.col_block * bn;
+  c.kb_begin = split * P.kblocks_per_split;
+  c.kb_end = min(c.kb_begin + P.kblocks_per_split, P.kblocks_total);
+  return c;
+}
+
 template <int BN, int AMN, int BMN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 64 ? 2 : 1))
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-               int kblocks_total, int kblocks_per_split, int tiles_m, int tiles_n, int total_tiles, int num_stages,
-               EpiArgs ep) {
+gemm_tc_kernel(const __grid_constant__ GroupArgs ga, int num_stages) {
   using Cfg = TileCfg<BN>;
   static_assert(BN % 64 == 0 || BMN == 0, "MN-major B needs 64-wide atoms");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -143,16 +178,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tiles_mn = tiles_m * tiles_n;
   // every CTA owns a contiguous range of tiles (m fastest): it streams down one column block of the output, so the
   // B tile (weights) stays hot and per-column epilogue state (bias-gradient sums) is flushed at most twice
+  const int total_tiles = ga.total_tiles;
   const int tiles_per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
   const int t_begin = blockIdx.x * tiles_per_cta;
   const int t_end = min(total_tiles, t_begin + tiles_per_cta);
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < ga.n; ++i) {
+      tma_prefetch_desc(&ga.p[i].tmA);
+      tma_prefetch_desc(&ga.p[i].tmB);
+    }
     for (int s = 0; s < num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -175,11 +212,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int it = 0;  // running k-block counter over all my tiles (ring position)
       for (int t = t_begin; t < t_end; ++t) {
-        const int split = t / tiles_mn, rem = t - split * tiles_mn;
-        const int m0 = (rem % tiles_m) * BM, n0 = (rem / tiles_m) * BN;  // m fastest: a CTA stays in one column block
-        const int kb_begin = split * kblocks_per_split;
-        const int kb_end = min(kb_begin + kblocks_per_split, kblocks_total);
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const TileCoord tc = decode_tile(ga, t, BN);
+        const CUtensorMap* tmA = &ga.p[tc.pi].tmA;
+        const CUtensorMap* tmB = &ga.p[tc.pi].tmB;
+        for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb, ++it) {
           const int s = it % num_stages;
           const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -188,16 +224,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + Cfg::kABytes;
           const int k0 = kb * BK;
           if constexpr (AMN == 0) {
-            tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {64 k, 128 rows}
+            tma_load_2d(sa, tmA, &full_bar[s], k0, tc.m0);  // box {64 k, 128 rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], m0 + 64 * j, k0);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), tmA, &full_bar[s], tc.m0 + 64 * j, k0);
           }
           if constexpr (BMN == 0) {
-            tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {64 k, BN rows}
+            tma_load_2d(sb, tmB, &full_bar[s], k0, tc.n0);  // box {64 k, BN rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + 64 * j, k0);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), tmB, &full_bar[s], tc.n0 + 64 * j, k0);
           }
         }
       }
@@ -208,9 +244,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, AMN, BMN);
       int it = 0, lt = 0;
       for (int t = t_begin; t < t_end; ++t, ++lt) {
-        const int split = t / tiles_mn;
-        const int kb_begin = split * kblocks_per_split;
-        const int nkb = min(kb_begin + kblocks_per_split, kblocks_total) - kb_begin;
+        const TileCoord tc = decode_tile(ga, t, BN);
+        const int nkb = tc.kb_end - tc.kb_begin;
         const int buf = lt & 1;
         mbar_wait(&tmem_empty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
         tc_fence_after();
@@ -240,7 +275,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ epilogue (8 warps) ------------------------------
     const int ew = warp - 2;             // 0..7
     const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = ew >> 2;            // column half handled in phase 1
+    const int half = ew >> 2;            // which 32-column TMEM chunks (even / odd) this warp moves in phase 1
     const int et = ew * 32 + lane;       // 0..255
     constexpr int VPR = BN / 4;              // float4 per tile row
     constexpr int RPP = EPI_THREADS / VPR;   // rows per pass
@@ -253,8 +288,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
     int lt = 0;
     for (int t = t_begin; t < t_end; ++t, ++lt) {
-      const int split = t / tiles_mn, rem = t - split * tiles_mn;
-      const int m0 = (rem % tiles_m) * BM, n0 = (rem / tiles_m) * BN;
+      const TileCoord tc = decode_tile(ga, t, BN);
+      const TileProblem& P = ga.p[tc.pi];
+      const EpiArgs& ep = P.ep;
+      const int M = P.M, N = P.N;
+      const int m0 = tc.m0, n0 = tc.n0;
       const int col = n0 + cv * 4;
       const bool col_ok = active && col < N;
       // prefetch the auxiliary operand of this tile (its addresses do not depend on the accumulators)
@@ -315,9 +353,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if constexpr (MODE == SCOT_EPI_GELU_BWD) {
-          // column sums (bias gradient): flush when the next tile of this CTA is in a different column block
-          const int tn = t + 1;
-          const bool last_of_col = (tn >= t_end) || ((tn % tiles_mn) / tiles_m) != (rem / tiles_m);
+          // column sums (bias gradient): flush when the next tile of this CTA is in a different column block / problem
+          bool last_of_col = (t + 1 >= t_end);
+          if (!last_of_col) {
+            const TileCoord nx = decode_tile(ga, t + 1, BN);
+            last_of_col = nx.pi != tc.pi || nx.col_block != tc.col_block;
+          }
           if (last_of_col && ep.colsum != nullptr) {
             atomicAdd(ep.colsum + col + 0, csum.x);
             atomicAdd(ep.colsum + col + 1, csum.y);
@@ -407,36 +448,59 @@ int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, 
 
 int g_num_sms = 0;
 
+struct HostProblem {
+  const void* A;
+  long lda;
+  const void* B;
+  long ldb;
+  int M, N, K;
+  EpiArgs ep;
+};
+
 template <int BN, int AMN, int BMN, int MODE>
-int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
-              cudaStream_t stream) {
+int launch_tc_group(const HostProblem* hp, int n, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
-  CUtensorMap tmA, tmB;
-  int rc;
-  if (AMN == 0) rc = make_tmap(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
-  else rc = make_tmap(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
-  if (rc) return rc;
-  if (BMN == 0) rc = make_tmap(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
-  else rc = make_tmap(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
-  if (rc) return rc;
-
-  const int tiles_m = ceil_div(M, BM), tiles_n = ceil_div(N, BN);
-  const int kblocks = ceil_div(K, BK);
-  int splits = 1;
-  if (MODE == SCOT_EPI_ATOMIC_F32) {
-    // split the (long) reduction so that there are about two tiles of work per SM
-    const int target = 2 * g_num_sms;
-    splits = target / (tiles_m * tiles_n);
-    if (splits < 1) splits = 1;
-    if (splits > kblocks) splits = kblocks;
+  SCOT_REQUIRE(n >= 1 && n <= kMaxGroup, "gemm group: 1..%d problems", kMaxGroup);
+  GroupArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.n = n;
+  // tiles of all problems first (to size the K splits of the reduction-heavy wgrad mode for the whole group)
+  int base_tiles = 0;
+  for (int i = 0; i < n; ++i) base_tiles += ceil_div(hp[i].M, BM) * ceil_div(hp[i].N, BN);
+  int total = 0;
+  for (int i = 0; i < n; ++i) {
+    TileProblem& P = ga.p[i];
+    const HostProblem& h = hp[i];
+    int rc;
+    if (AMN == 0) rc = make_tmap(&P.tmA, h.A, (uint64_t)h.K, (uint64_t)h.M, (uint64_t)h.lda, BK, BM);
+    else rc = make_tmap(&P.tmA, h.A, (uint64_t)h.M, (uint64_t)h.K, (uint64_t)h.lda, 64, BK);
+    if (rc) return rc;
+    if (BMN == 0) rc = make_tmap(&P.tmB, h.B, (uint64_t)h.K, (uint64_t)h.N, (uint64_t)h.ldb, BK, BN);
+    else rc = make_tmap(&P.tmB, h.B, (uint64_t)h.N, (uint64_t)h.K, (uint64_t)h.ldb, 64, BK);
+    if (rc) return rc;
+    P.M = h.M;
+    P.N = h.N;
+    P.tiles_m = ceil_div(h.M, BM);
+    P.tiles_n = ceil_div(h.N, BN);
+    P.kblocks_total = ceil_div(h.K, BK);
+    int splits = 1;
+    if (MODE == SCOT_EPI_ATOMIC_F32) {
+      // split the (long) reduction so that the whole group has about two tiles of work per SM
+      splits = (2 * g_num_sms) / base_tiles;
+      if (splits < 1) splits = 1;
+      if (splits > P.kblocks_total) splits = P.kblocks_total;
+    }
+    P.kblocks_per_split = ceil_div(P.kblocks_total, splits);
+    splits = ceil_div(P.kblocks_total, P.kblocks_per_split);  // no empty split
+    P.tile_begin = total;
+    P.ep = h.ep;
+    total += P.tiles_m * P.tiles_n * splits;
   }
-  int kps = ceil_div(kblocks, splits);
-  splits = ceil_div(kblocks, kps);  // no empty split
-  const int total_tiles = tiles_m * tiles_n * splits;
+  ga.total_tiles = total;
 
-  // smem: barriers + operand ring + dedicated fp32 staging tile (the ring keeps running during the epilogue)
   // BN <= 64: two CTAs per SM (two independent epilogue pipelines hide each other's latencies)
   constexpr int kCtasPerSm = BN <= 64 ? 2 : 1;
+  // smem: barriers + operand ring + dedicated fp32 staging tile (the ring keeps running during the epilogue)
   const size_t fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + (size_t)Cfg::kStagingBytes;
   const size_t budget = (size_t)(227 * 1024) / kCtasPerSm - (kCtasPerSm > 1 ? 1024 : 0);
   int stages = (int)((budget - fixed) / Cfg::kStageBytes);
@@ -450,11 +514,17 @@ int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, in
     attr_done = true;
   }
   const int max_ctas = g_num_sms * kCtasPerSm;
-  const int grid = total_tiles < max_ctas ? total_tiles : max_ctas;
-  SCOT_CHECK_CUDA(scot_launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, M, N, kblocks, kps, tiles_m,
-                                  tiles_n, total_tiles, stages, ep));
+  const int grid = total < max_ctas ? total : max_ctas;
+  SCOT_CHECK_CUDA(scot_launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, ga, stages));
   SCOT_LAUNCH_CHECK();
   return 0;
+}
+
+template <int BN, int AMN, int BMN, int MODE>
+int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
+              cudaStream_t stream) {
+  HostProblem h{A, lda, B, ldb, M, N, K, ep};
+  return launch_tc_group<BN, AMN, BMN, MODE>(&h, 1, stream);
 }
 
 template <int AMN, int BMN, int MODE>
@@ -493,6 +563,43 @@ int launch_simt(const void* A, long lda, int amn, const void* B, long ldb, int b
 }
 
 }  // namespace
+
+// Weight gradients of up to four Linear layers in ONE launch: dW_i[N_i, K_i] += dY_i[tok, N_i]^T X_i[tok, K_i]
+// (both operands MN-major, split reduction over the tokens, fp32 red.add into the gradient buffer).
+int scot_gemm_wgrad_group_launch(const ScotWgradProblem* probs, int n, int impl, cudaStream_t stream) {
+  SCOT_REQUIRE(probs && n >= 1 && n <= kMaxGroup, "wgrad group: 1..%d problems", kMaxGroup);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    SCOT_CHECK_CUDA(cudaGetDevice(&dev));
+    SCOT_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  bool narrow = false, wide = false;
+  for (int i = 0; i < n; ++i) {
+    const ScotWgradProblem& q = probs[i];
+    SCOT_REQUIRE(q.dY && q.X && q.dW && q.tokens > 0 && q.n_out > 0 && q.n_in > 0, "wgrad group: bad problem %d", i);
+    SCOT_REQUIRE(q.n_in % 4 == 0 && q.ld_dy % 8 == 0 && q.ld_x % 8 == 0, "wgrad group: alignment (problem %d)", i);
+    (q.n_in > 64 ? wide : narrow) = true;
+  }
+  if (impl == SCOT_GEMM_SIMT || (narrow && wide)) {  // cross-check path / mixed tile widths: one launch per problem
+    for (int i = 0; i < n; ++i) {
+      const ScotWgradProblem& q = probs[i];
+      ScotEpilogue e{SCOT_EPI_ATOMIC_F32, nullptr, q.dW, q.ld_dw, nullptr, 0, nullptr, 0, nullptr};
+      int rc = scot_gemm_launch(q.dY, q.ld_dy, 1, q.X, q.ld_x, 1, q.n_out, q.n_in, (int)q.tokens, &e, impl, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  int rc = get_encode_fn();
+  if (rc) return rc;
+  HostProblem hp[kMaxGroup];
+  for (int i = 0; i < n; ++i) {
+    const ScotWgradProblem& q = probs[i];
+    hp[i] = HostProblem{q.dY, q.ld_dy, q.X, q.ld_x, q.n_out, q.n_in, (int)q.tokens,
+                        EpiArgs{nullptr, q.dW, q.ld_dw, nullptr, 0, nullptr, 0, nullptr}};
+  }
+  if (wide) return launch_tc_group<128, 1, 1, SCOT_EPI_ATOMIC_F32>(hp, n, stream);
+  return launch_tc_group<64, 1, 1, SCOT_EPI_ATOMIC_F32>(hp, n, stream);
+}
 
 int scot_gemm_launch(const void* A, long lda, int a_mn_major, const void* B, long ldb, int b_mn_major, int M, int N,
                      int K, const ScotEpilogue* e, int impl, cudaStream_t stream) {

@@ -5,6 +5,7 @@
 
 int scot_gemm_launch(const void* A, long lda, int a_mn_major, const void* B, long ldb, int b_mn_major, int M, int N,
                      int K, const ScotEpilogue* e, int impl, cudaStream_t stream);
+int scot_gemm_wgrad_group_launch(const ScotWgradProblem* probs, int n, int impl, cudaStream_t stream);
 
 // norm.cu
 int scot_cln_fwd_launch(const float* z, const float* residual, const float* time, const float* aw, const float* ab,

@@ -85,6 +85,22 @@ def test_gemm_gelu_and_backward(L, impl):
     assert rel(cs, out.float().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("tok,C", [(4096, 96), (1024, 768), (512, 48)])
+def test_gemm_wgrad_group(L, impl, tok, C):
+    """the four weight gradients of a transformer block in one launch (mixed tile widths fall back to four)"""
+    torch.manual_seed(tok + C)
+    H = 4 * C
+    mk = lambda n: torch.randn(tok, n, device=dev).bfloat16()
+    probs = [(mk(C), mk(H), torch.zeros(C, H, device=dev)), (mk(H), mk(C), torch.zeros(H, C, device=dev)),
+             (mk(C), mk(C), torch.zeros(C, C, device=dev)), (mk(3 * C), mk(C), torch.zeros(3 * C, C, device=dev))]
+    L.wgrad_group(probs, impl=impl)
+    L.wgrad_group(probs[:2], impl=impl)  # accumulates
+    for k, (dY, X, dW) in enumerate(probs):
+        ref = dY.float().t() @ X.float() * (2 if k < 2 else 1)
+        assert rel(dW, ref) < 2e-5, k
+
+
 # ------------------------------------------------------------------------------------------------------
 # (conditional) layer norm
 # ------------------------------------------------------------------------------------------------------
