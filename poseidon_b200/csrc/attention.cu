@@ -676,43 +676,46 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
   }
 }
 
-// second stage of the bias-gradient reduction: sum the per-CTA dumps over chunks and fold the N x N
-// positions onto the (2ws-1)^2 table through the relative position index (HF:512-523).
+// Folds the accumulated N x N bias gradient of one head onto the (2ws-1)^2 table through the relative position index
+// (HF:512-523). Gather form: one thread per table entry (head, dp, dq) walks the <= ws^2 (query, key) pairs with that
+// displacement, reads them from the fragment-ordered accumulation buffer (and clears them for the next layer): no
+// atomics, deterministic.
 template <int WS, int NWARP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 attn_bias_reduce_kernel(float* __restrict__ partial, float* __restrict__ dtab, int heads, int chunks) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int N = WS * WS, MT = N / 16;
-  constexpr int RG = (MT / NWARP) > 1 ? (MT / NWARP) : 1;
-  constexpr int KC = N < 64 ? N : 64, NT = KC / 8;
-  constexpr int TABN = (2 * WS - 1) * (2 * WS - 1);
-  constexpr int PER_HEAD = RG * NWARP * 16 * N;
-  __shared__ float st[TABN];
-  const int h = blockIdx.x;
-  for (int i = threadIdx.x; i < TABN; i += blockDim.x) st[i] = 0.f;
-  __syncthreads();
-  const int per_cta = (PER_HEAD + gridDim.y - 1) / gridDim.y;
-  const int p0 = blockIdx.y * per_cta, p1 = min(PER_HEAD, p0 + per_cta);
-  for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
-    float* src = partial + (long)h * PER_HEAD + p;
-    const float v = *src;
-    *src = 0.f;  // leave the accumulation buffer clean for the next layer
-    // decode slot -> (row m, col n)
-    const int rgw = p / (16 * N);      // rg * NWARP + warp
-    const int slot = p - rgw * 16 * N;
-    const int lane = slot & 31;
-    const int q = slot >> 5;           // (kc*NT + nt)*4 + r
-    const int r = q & 3, nt_all = q >> 2;
-    const int rg = rgw / NWARP, warp = rgw - rg * NWARP;
-    const int mt = (NWARP / MT > 1) ? (warp % MT) : (rg * NWARP + warp);
-    const int m = mt * 16 + (lane >> 2) + ((r >> 1) << 3);
-    const int n = nt_all * 8 + 2 * (lane & 3) + (r & 1);
-    (void)NT;
-    atomicAdd(&st[bias_rowbase<WS>(m) - bias_coloff<WS>(n)], v);
+  constexpr int SIDE = 2 * WS - 1, TABN = SIDE * SIDE;
+  constexpr int RGW = (MT >= NWARP) ? MT : NWARP;        // warp slots per head in the accumulation buffer
+  constexpr int COPIES = (MT >= NWARP) ? 1 : NWARP / MT;  // several windows per CTA -> the same tile appears COPIES times
+  constexpr int PER_HEAD = RGW * 16 * N;
+  (void)chunks;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= TABN * heads) return;
+  const int r = idx / heads, h = idx - r * heads;
+  const int dp = r / SIDE - (WS - 1), dq = r % SIDE - (WS - 1);  // (p_query - p_key, q_query - q_key)
+  float* base = partial + (long)h * PER_HEAD;
+  float acc = 0.f;
+  const int pm_lo = dp > 0 ? dp : 0, pm_hi = dp < 0 ? WS + dp : WS;
+  const int qm_lo = dq > 0 ? dq : 0, qm_hi = dq < 0 ? WS + dq : WS;
+  for (int pm = pm_lo; pm < pm_hi; ++pm) {
+    for (int qm = qm_lo; qm < qm_hi; ++qm) {
+      const int m = pm * WS + qm, n = (pm - dp) * WS + (qm - dq);
+      // fragment position of (m, n): tile m/16, lane (m%8)*4 + (n%8)/2, register ((m%16)/8)*2 + n%2, column tile n/8
+      const int mt = m >> 4;
+      const int lane = ((m & 7) << 2) | ((n & 7) >> 1);
+      const int reg = (((m >> 3) & 1) << 1) | (n & 1);
+      const int slot = (((n >> 3) << 2) + reg) * 32 + lane;
+#pragma unroll
+      for (int cpy = 0; cpy < COPIES; ++cpy) {
+        float* src = base + (long)(mt + cpy * MT) * 16 * N + slot;
+        acc += *src;
+        *src = 0.f;
+      }
+    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < TABN; i += blockDim.x) atomicAdd(dtab + i * heads + h, st[i]);
+  atomicAdd(dtab + r * heads + h, acc);  // dtab is zero at the start of the backward pass: plain accumulate
 }
 
 // =================================================================================================
@@ -998,9 +1001,9 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
   SCOT_CHECK_CUDA(scot_launch_pdl(k2, grid2, dim3(NWARP * 32), C2::smem, st, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
                                   tab2, alpha, (bf16*)dqkv, g_vbias, g, total_windows, wpc2));
   SCOT_LAUNCH_CHECK();
-  const int red_y = WS == 16 ? 32 : (WS == 8 ? 4 : 1);
-  SCOT_CHECK_CUDA(scot_launch_pdl(attn_bias_reduce_kernel<WS, NWARP>, dim3(g.heads, red_y), dim3(256), 0, st, partial, dtab, g.heads,
-                                  chunks));
+  constexpr int kTab = (2 * WS - 1) * (2 * WS - 1);
+  SCOT_CHECK_CUDA(scot_launch_pdl(attn_bias_reduce_kernel<WS, NWARP>, dim3(ceil_div(kTab * g.heads, 128)), dim3(128), 0, st, partial,
+                                  dtab, g.heads, chunks));
   SCOT_LAUNCH_CHECK();
   return 0;
 }

@@ -489,6 +489,12 @@ int launch_tc_group(const HostProblem* hp, int n, cudaStream_t stream) {
       splits = (2 * g_num_sms) / base_tiles;
       if (splits < 1) splits = 1;
       if (splits > P.kblocks_total) splits = P.kblocks_total;
+    } else if (MODE == SCOT_EPI_RMW_F32) {
+      // "+=" epilogue (red.add): the reduction can be split as well. Deep stages have few output tiles but K up to
+      // 3072, i.e. >1 MB streamed through a single SM per tile; keep at least 4 k-blocks per split.
+      splits = (2 * g_num_sms) / base_tiles;
+      if (splits > P.kblocks_total / 4) splits = P.kblocks_total / 4;
+      if (splits < 1) splits = 1;
     }
     P.kblocks_per_split = ceil_div(P.kblocks_total, splits);
     splits = ceil_div(P.kblocks_total, P.kblocks_per_split);  // no empty split
