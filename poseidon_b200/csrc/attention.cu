@@ -691,31 +691,33 @@ attn_bias_reduce_kernel(float* __restrict__ partial, float* __restrict__ dtab, i
   constexpr int COPIES = (MT >= NWARP) ? 1 : NWARP / MT;  // several windows per CTA -> the same tile appears COPIES times
   constexpr int PER_HEAD = RGW * 16 * N;
   (void)chunks;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per table entry; lanes split the (query, key) pairs of that displacement
+  const int lane_id = threadIdx.x & 31;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (idx >= TABN * heads) return;
   const int r = idx / heads, h = idx - r * heads;
   const int dp = r / SIDE - (WS - 1), dq = r % SIDE - (WS - 1);  // (p_query - p_key, q_query - q_key)
   float* base = partial + (long)h * PER_HEAD;
   float acc = 0.f;
-  const int pm_lo = dp > 0 ? dp : 0, pm_hi = dp < 0 ? WS + dp : WS;
-  const int qm_lo = dq > 0 ? dq : 0, qm_hi = dq < 0 ? WS + dq : WS;
-  for (int pm = pm_lo; pm < pm_hi; ++pm) {
-    for (int qm = qm_lo; qm < qm_hi; ++qm) {
-      const int m = pm * WS + qm, n = (pm - dp) * WS + (qm - dq);
-      // fragment position of (m, n): tile m/16, lane (m%8)*4 + (n%8)/2, register ((m%16)/8)*2 + n%2, column tile n/8
-      const int mt = m >> 4;
-      const int lane = ((m & 7) << 2) | ((n & 7) >> 1);
-      const int reg = (((m >> 3) & 1) << 1) | (n & 1);
-      const int slot = (((n >> 3) << 2) + reg) * 32 + lane;
+  const int pm_lo = dp > 0 ? dp : 0, np = WS - (dp < 0 ? -dp : dp);
+  const int qm_lo = dq > 0 ? dq : 0, nq = WS - (dq < 0 ? -dq : dq);
+  for (int i = lane_id; i < np * nq; i += 32) {
+    const int pm = pm_lo + i / nq, qm = qm_lo + i % nq;
+    const int m = pm * WS + qm, n = (pm - dp) * WS + (qm - dq);
+    // fragment position of (m, n): tile m/16, lane (m%8)*4 + (n%8)/2, register ((m%16)/8)*2 + n%2, column tile n/8
+    const int mt = m >> 4;
+    const int lane = ((m & 7) << 2) | ((n & 7) >> 1);
+    const int reg = (((m >> 3) & 1) << 1) | (n & 1);
+    const int slot = (((n >> 3) << 2) + reg) * 32 + lane;
 #pragma unroll
-      for (int cpy = 0; cpy < COPIES; ++cpy) {
-        float* src = base + (long)(mt + cpy * MT) * 16 * N + slot;
-        acc += *src;
-        *src = 0.f;
-      }
+    for (int cpy = 0; cpy < COPIES; ++cpy) {
+      float* src = base + (long)(mt + cpy * MT) * 16 * N + slot;
+      acc += *src;
+      *src = 0.f;
     }
   }
-  atomicAdd(dtab + r * heads + h, acc);  // dtab is zero at the start of the backward pass: plain accumulate
+  acc = warp_sum(acc);
+  if (lane_id == 0) atomicAdd(dtab + r * heads + h, acc);  // dtab is zero at the start of the backward pass
 }
 
 // =================================================================================================
@@ -1002,7 +1004,7 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
                                   tab2, alpha, (bf16*)dqkv, g_vbias, g, total_windows, wpc2));
   SCOT_LAUNCH_CHECK();
   constexpr int kTab = (2 * WS - 1) * (2 * WS - 1);
-  SCOT_CHECK_CUDA(scot_launch_pdl(attn_bias_reduce_kernel<WS, NWARP>, dim3(ceil_div(kTab * g.heads, 128)), dim3(128), 0, st, partial,
+  SCOT_CHECK_CUDA(scot_launch_pdl(attn_bias_reduce_kernel<WS, NWARP>, dim3(ceil_div(kTab * g.heads, 4)), dim3(128), 0, st, partial,
                                   dtab, g.heads, chunks));
   SCOT_LAUNCH_CHECK();
   return 0;
