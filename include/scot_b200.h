@@ -159,6 +159,10 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
  * grad_loss: device scalar or NULL; grad_pred: [B,Cout,H,W] or NULL. Gradients are accumulated, never zeroed. */
 int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void* arena, const float* grad_loss,
                          const float* grad_pred, int gemm_impl, void* stream);
+/* Re-binds the tensors the next scot_engine_backward reads (the inputs / prediction of a forward that was replayed
+ * from a CUDA graph, where the host-side bookkeeping of scot_engine_forward did not run). Host-only, no launch. */
+int scot_engine_bind_io(ScotEngine* e, const float* pixel_values, const float* time, const float* labels,
+                        const uint8_t* mask, int mask_mode, float* pred);
 
 #ifdef __cplusplus
 }

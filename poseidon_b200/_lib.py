@@ -148,6 +148,8 @@ def _declare_engine(lib):
     lib.scot_engine_forward.restype = i
     lib.scot_engine_backward.argtypes = [vp] * 6 + [i, vp]
     lib.scot_engine_backward.restype = i
+    lib.scot_engine_bind_io.argtypes = [vp] * 5 + [i, vp]
+    lib.scot_engine_bind_io.restype = i
 
 
 _declare_base = _declare
@@ -295,6 +297,10 @@ class Engine:
         check(self._lib.scot_engine_forward(self.handle, ptr(params), ptr(arena), ptr(pixel_values), ptr(time),
                                             ptr(labels), ptr(mask), mask_mode, ptr(pred), ptr(loss), impl, cur_stream()),
               "scot_engine_forward")
+
+    def bind_io(self, pixel_values, time, labels, mask, mask_mode, pred):
+        check(self._lib.scot_engine_bind_io(self.handle, ptr(pixel_values), ptr(time), ptr(labels), ptr(mask), mask_mode,
+                                            ptr(pred)), "scot_engine_bind_io")
 
     def backward(self, params, grads, arena, grad_loss, grad_pred, impl=GEMM_TCGEN05):
         check(self._lib.scot_engine_backward(self.handle, ptr(params), ptr(grads), ptr(arena), ptr(grad_loss),

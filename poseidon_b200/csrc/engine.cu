@@ -686,6 +686,19 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
   return 0;
 }
 
+int scot_engine_bind_io(ScotEngine* e, const float* pixel_values, const float* time, const float* labels,
+                        const uint8_t* mask, int mask_mode, float* pred) {
+  SCOT_REQUIRE(e && pixel_values && pred, "engine_bind_io: null pointer");
+  e->last_pixels = pixel_values;
+  e->last_time = time;
+  e->last_labels = labels;
+  e->last_mask = mask;
+  e->last_mask_mode = labels ? mask_mode : 0;
+  e->last_pred = pred;
+  e->have_forward = true;
+  return 0;
+}
+
 int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void* arena, const float* grad_loss,
                          const float* grad_pred, int gemm_impl, void* stream) {
   SCOT_REQUIRE(e && params && grads && arena, "engine_backward: null pointer");

@@ -255,18 +255,85 @@ class ConvNeXtBlock(_Holder):
 # ------------------------------------------------------------------------------------------------------
 # autograd bridge
 # ------------------------------------------------------------------------------------------------------
+class _GraphSlot:
+    """Static device buffers + captured CUDA graphs for one call signature of `ScOT.forward`
+    (batch, labels?, mask mode, grad?). The first call of a signature runs eagerly (one-time kernel
+    attribute setup), the second captures `engine.forward` (and `engine.backward`) into CUDA graphs,
+    later calls copy the inputs into the static buffers and replay: ~1200 kernel launches become one
+    `cudaGraphLaunch`, so the step time no longer depends on the speed of the host."""
+
+    def __init__(self, model, st, batch, has_labels, mask_mode, mask_shape):
+        cfg = model.config
+        dev = st["device"]
+        s = cfg.image_size
+        self.calls = 0
+        self.x = torch.zeros(batch, cfg.num_channels, s, s, device=dev)
+        self.t = torch.zeros(batch, device=dev) if cfg.use_conditioning else None
+        self.y = torch.zeros(batch, cfg.num_out_channels, s, s, device=dev) if has_labels else None
+        self.mask = torch.zeros(mask_shape, dtype=torch.uint8, device=dev) if mask_mode else None
+        self.mask_mode = mask_mode
+        self.pred = torch.empty(batch, cfg.num_out_channels, s, s, device=dev)
+        self.loss = torch.zeros(1, device=dev) if has_labels else None
+        self.gl = torch.ones(1, device=dev)
+        self.g_fwd = None
+        self.g_bwd = None
+
+    def capture(self, model, st, with_backward):
+        eng = st["engine"]
+        torch.cuda.synchronize(st["device"])
+        self.g_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd):
+            eng.forward(st["flat"], st["arena"], self.x, self.t, self.y, self.mask, self.mask_mode, self.pred, self.loss,
+                        model.gemm_impl)
+        if with_backward and self.loss is not None:
+            self.g_bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
+                eng.backward(st["flat"], st["gflat"], st["arena"], self.gl, None, model.gemm_impl)
+
+
 class _ScOTFunction(torch.autograd.Function):
-    """One node for the whole model: forward/backward are single calls into the native engine."""
+    """One node for the whole model: forward/backward are single calls into the native engine (or
+    replays of their CUDA graphs, see `_GraphSlot`)."""
 
     @staticmethod
     def forward(ctx, model, pixel_values, time, labels, mask, mask_mode, *params):
         st = model._state
         eng = st["engine"]
+        ctx.set_materialize_grads(False)  # an unused output (the prediction, usually) arrives as None in backward
+        ctx.model = model
+        ctx.slot = None
+        need_grad = len(params) > 0
+        slot = None
+        if model.use_cuda_graphs and not torch.cuda.is_current_stream_capturing():
+            key = (labels is not None, mask_mode, tuple(mask.shape) if mask is not None else None, need_grad)
+            slot = st["slots"].get(key)
+            if slot is None:
+                slot = st["slots"][key] = _GraphSlot(model, st, pixel_values.shape[0], labels is not None, mask_mode,
+                                                     tuple(mask.shape) if mask is not None else None)
+            slot.calls += 1
+            if slot.calls < 2:
+                slot = None
+        if slot is not None:
+            if slot.g_fwd is None:
+                slot.capture(model, st, need_grad)
+            slot.x.copy_(pixel_values, non_blocking=True)
+            if slot.t is not None:
+                slot.t.copy_(time, non_blocking=True)
+            if slot.y is not None:
+                slot.y.copy_(labels, non_blocking=True)
+            if slot.mask is not None:
+                slot.mask.copy_(mask, non_blocking=True)
+            slot.g_fwd.replay()
+            ctx.slot = slot
+            # the static outputs are overwritten by the next replay: hand out copies
+            pred = slot.pred.clone()
+            if slot.loss is None:
+                return pred, None
+            return pred, slot.loss.clone().reshape(())
         pred = torch.empty((pixel_values.shape[0], model.config.num_out_channels) + tuple(pixel_values.shape[2:]),
                            device=pixel_values.device, dtype=torch.float32)
         loss = torch.zeros(1, device=pixel_values.device, dtype=torch.float32) if labels is not None else None
         eng.forward(st["flat"], st["arena"], pixel_values, time, labels, mask, mask_mode, pred, loss, model.gemm_impl)
-        ctx.model = model
         ctx.keep = (pixel_values, time, labels, mask, pred)  # the engine reads these again in backward
         if loss is None:
             return pred, None
@@ -277,6 +344,7 @@ class _ScOTFunction(torch.autograd.Function):
         model = ctx.model
         st = model._state
         eng = st["engine"]
+        nret = 6 + len(st["views"])
         gl = None
         if grad_loss is not None:
             gl = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
@@ -284,18 +352,26 @@ class _ScOTFunction(torch.autograd.Function):
         if grad_pred is not None:
             gp = grad_pred.detach().to(torch.float32).contiguous()
         if gl is None and gp is None:
-            return (None,) * (6 + len(st["views"]))
+            return (None,) * nret
         gflat = st["gflat"]
         assign = model.grad_mode == "assign"
         if not assign:
             gflat.zero_()  # autograd accumulates the returned tensors into .grad itself
-        eng.backward(st["flat"], gflat, st["arena"], gl, gp, model.gemm_impl)
+        slot = ctx.slot
+        if slot is not None and slot.g_bwd is not None and gp is None:
+            slot.gl.copy_(gl, non_blocking=True)
+            slot.g_bwd.replay()
+        else:
+            if slot is not None:
+                # eager backward after a replayed forward: point the engine at the static buffers of that forward
+                eng.bind_io(slot.x, slot.t, slot.y, slot.mask, slot.mask_mode, slot.pred)
+            eng.backward(st["flat"], gflat, st["arena"], gl, gp, model.gemm_impl)
         if assign:
             # gradients are views of the flat buffer; accumulation across micro-batches happens in place
             for p, gv in zip(st["plist"], st["gviews"]):
                 if p.grad is None:
                     p.grad = gv
-            return (None,) * (6 + len(st["views"]))
+            return (None,) * nret
         return (None,) * 6 + tuple(st["gviews"])
 
 
@@ -347,6 +423,8 @@ class ScOT(PreTrainedModel):
         self._state = None
         self.grad_mode = "autograd"  # "autograd": grads flow through autograd (DDP/hooks work); "assign": .grad = flat views
         self.gemm_impl = _lib.GEMM_TCGEN05
+        # replay CUDA graphs of the engine's forward / backward from the second call of a signature on (_GraphSlot)
+        self.use_cuda_graphs = True
         self.post_init()
 
     # ---- HF plumbing ------------------------------------------------------------------------------
@@ -453,7 +531,7 @@ class ScOT(PreTrainedModel):
         shift = (-arena.data_ptr()) % 256
         arena = arena[shift:shift + eng.workspace_bytes]
         self._state = dict(device=device, batch=batch, engine=eng, flat=flat, gflat=gflat, plist=plist, views=views,
-                           gviews=gviews, arena=arena)
+                           gviews=gviews, arena=arena, slots={})
         return self._state
 
     @property

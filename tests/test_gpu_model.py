@@ -155,4 +155,38 @@ def test_assign_grad_mode_accumulates_like_autograd():
     engine_run(rec, cfg, model, inputs).loss.backward()
     engine_run(rec, cfg, model, inputs).loss.backward()  # second micro-batch accumulates in place
     for k, p in model.named_parameters():
-        assert rel(p.grad, 2 * g_auto[k]) < 1e-3, k
+        assert rel(p.grad, 2 * g_auto[k]) < 3e-3, k  # fp32 atomics + bf16 re-rounding downstream: not bit-reproducible
+
+
+def test_cuda_graph_replay_matches_eager():
+    """From the second call of a signature on, ScOT.forward / backward replay CUDA graphs over static buffers
+    (model.py `_GraphSlot`); results must equal the eager launches of the same kernels on fresh inputs."""
+    rec, cfg, w, model, inputs = build("tiny_ln")
+    _, _, _, eager, _ = build("tiny_ln")
+    eager.use_cuda_graphs = False
+    x, t, y, pm = inputs
+    for step in range(4):
+        g = torch.Generator().manual_seed(100 + step)
+        xs = (x + 0.1 * torch.randn(x.shape, generator=g), t, y + 0.1 * torch.randn(y.shape, generator=g), pm)
+        outs = []
+        for m in (model, eager):
+            for p in m.parameters():
+                p.grad = None
+            out = engine_run(rec, cfg, m, xs)
+            out.loss.backward()
+            outs.append(out)
+        assert torch.equal(outs[0].output, outs[1].output), step
+        # the loss / gradient reductions use fp32 atomics: the summation order differs from run to run
+        assert abs(float(outs[0].loss.detach()) - float(outs[1].loss.detach())) < 1e-5 * abs(float(outs[1].loss.detach()))
+        for (k, p), (_, q) in zip(model.named_parameters(), eager.named_parameters()):
+            assert rel(p.grad, q.grad) < 3e-3, (step, k)
+    slots = model._state["slots"]
+    assert len(slots) == 1 and next(iter(slots.values())).g_bwd is not None
+    # inference signature (no labels, no grad) gets its own slot; outputs are copies, not the static buffer
+    with torch.no_grad():
+        a = model(pixel_values=x.cuda(), time=t.cuda()).output
+        b = model(pixel_values=x.cuda(), time=t.cuda()).output
+        c = model(pixel_values=(x + 1).cuda(), time=t.cuda()).output
+        e = eager(pixel_values=(x + 1).cuda(), time=t.cuda()).output
+    assert torch.equal(a, b) and not torch.equal(a, c) and torch.equal(c, e)
+    assert len(slots) == 2
