@@ -92,7 +92,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // instead of erff's ~40-instruction path — the GEMM epilogues run on only four warps per CTA.
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
   const float ax = fabsf(x) * 0.70710678118654752440f;           // |x|/sqrt(2)
-  const float e2 = __expf(-0.5f * x * x);                         // exp(-x^2/2) = exp(-ax^2)
+  float e2;  // exp(-x^2/2) = 2^(-x^2 * log2(e)/2): one MUFU.EX2 (flush-to-zero: no denormal range fix-up code)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"((x * x) * -0.72134752044448170368f));
   float t;  // 1/(1 + p|x|/sqrt2): MUFU.RCP (1 ulp) is plenty for a result that is rounded to bf16
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
@@ -162,6 +163,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for the single-lane producer / MMA-issuer loops whose waits are long (they run ahead of the epilogue): back off so
+// that the polling does not take issue slots from the epilogue warps that share the scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — 2D tile load global -> shared, completion on an mbarrier
@@ -178,6 +197,34 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// 2D tile store shared -> global (bulk async group; rows / columns beyond the tensor bounds are clipped)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// 2D tile reduction shared -> global: global[tile] += smem[tile] (fp32 add performed by the L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// ... have completed entirely (global writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) before a bulk store reads them
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 (5th-gen tensor cores, TMEM)

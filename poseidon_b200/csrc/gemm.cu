@@ -20,6 +20,7 @@
 // These GEMMs have K = 96..3072 and are HBM/epilogue bound, so the design goal is to hide every fixed latency
 // (TMA round trip, TMEM allocation, store drain) behind the epilogue rather than to saturate the tensor pipe.
 // Tails in M, N and K are handled by TMA out-of-bounds zero fill + predicated stores.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -379,6 +380,259 @@ gemm_tc_kernel(const __grid_constant__ GroupArgs ga, int num_stages) {
 }
 
 // =================================================================================================
+// tcgen05 kernel, "async epilogue" variant for the bf16-output modes (BF16 / GELU / GELU_BWD)
+//
+// Same producer / MMA structure as gemm_tc_kernel with 128 x 64 tiles and two CTAs per SM, but NOTHING in the epilogue
+// waits on a global-memory round trip: the auxiliary operand (saved gelu') arrives by TMA through its own 2-stage
+// smem ring, and the outputs leave by TMA stores (cp.async.bulk.tensor, 128B-swizzled bf16 tiles) that drain while the
+// next tile is computed. In the epilogue one thread owns one accumulator row (tcgen05.ld 32x32b), so bias / GELU /
+// gelu' scaling are register-only; the bias-gradient column sums are taken from the bf16 tile in smem.
+// =================================================================================================
+struct AsyncArgs {
+  CUtensorMap tmA, tmB, tmAux, tmOut0, tmOut1;
+  int M, N, kblocks, tiles_m, tiles_n, total_tiles;
+  const float* bias;
+  float* colsum;
+  int has_out0;
+};
+
+constexpr int ABN = 64;                       // tile width of the async-epilogue kernel
+constexpr int kOutTileBytes = BM * ABN * 2;   // one 128 x 64 bf16 tile = 16 KB (128 B rows, 128B swizzle)
+constexpr int kAStageBytes = BM * BK * 2 + ABN * BK * 2;
+
+template <int BMN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_async_epi_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
+  constexpr bool kHasAux = (MODE == SCOT_EPI_GELU_BWD);
+  constexpr int kNumOut = (MODE == SCOT_EPI_GELU) ? 2 : 1;
+  constexpr int kAccCols = 64, kTmemCols = 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = empty_bar + 8;        // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint64_t* aux_full_bar = tmem_empty_bar + 2;    // [2]
+  uint64_t* aux_empty_bar = aux_full_bar + 2;     // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_empty_bar + 2);
+  uint8_t* tiles = smem + 1024;
+  uint8_t* aux_s = tiles + (size_t)num_stages * kAStageBytes;             // [2][16 KB] (GELU_BWD only)
+  uint8_t* out_s = aux_s + (kHasAux ? 2 * kOutTileBytes : 0);             // [kNumOut][16 KB]
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = ga.total_tiles;
+  const int tiles_per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = min(total_tiles, t_begin + tiles_per_cta);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&ga.tmA);
+    tma_prefetch_desc(&ga.tmB);
+    tma_prefetch_desc(&ga.tmOut1);
+    if (kHasAux) tma_prefetch_desc(&ga.tmAux);
+    if (kNumOut == 2 || MODE != SCOT_EPI_GELU) tma_prefetch_desc(&ga.tmOut0);
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], EPI_THREADS);
+      mbar_init(&aux_full_bar[b], 1);
+      mbar_init(&aux_empty_bar[b], EPI_THREADS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int it = 0, lt = 0;
+      for (int t = t_begin; t < t_end; ++t, ++lt) {
+        const int cb = t / ga.tiles_m;  // m fastest
+        const int m0 = (t - cb * ga.tiles_m) * BM, n0 = cb * ABN;
+        if constexpr (kHasAux) {
+          const int as = lt & 1;
+          mbar_wait_backoff(&aux_empty_bar[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&aux_full_bar[as], kOutTileBytes);
+          tma_load_2d(aux_s + as * kOutTileBytes, &ga.tmAux, &aux_full_bar[as], n0, m0);
+        }
+        for (int kb = 0; kb < ga.kblocks; ++kb, ++it) {
+          const int s = it % num_stages;
+          const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
+          mbar_wait_backoff(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], kAStageBytes);
+          uint8_t* sa = tiles + (size_t)s * kAStageBytes;
+          uint8_t* sb = sa + BM * BK * 2;
+          const int k0 = kb * BK;
+          tma_load_2d(sa, &ga.tmA, &full_bar[s], k0, m0);
+          if constexpr (BMN == 0) tma_load_2d(sb, &ga.tmB, &full_bar[s], k0, n0);
+          else tma_load_2d(sb, &ga.tmB, &full_bar[s], n0, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, ABN, 0, BMN);
+      int it = 0, lt = 0;
+      for (int t = t_begin; t < t_end; ++t, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait_backoff(&tmem_empty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * kAccCols);
+        for (int i = 0; i < ga.kblocks; ++i, ++it) {
+          const int s = it % num_stages;
+          const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
+          mbar_wait_backoff(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)s * kAStageBytes);
+          const uint32_t sb = sa + BM * BK * 2;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = (BMN == 0) ? umma_smem_desc(sb + k * 32, 16, 1024)
+                                           : umma_smem_desc(sb + k * 2048, BK * 128, 1024);
+            umma_bf16(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (8 warps) ------------------------------
+    const int ew = warp - 2;             // 0..7
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = ew >> 2;            // which 32-column half of the tile this warp converts
+    const int et = ew * 32 + lane;       // 0..255
+    const int row = q * 32 + lane;       // accumulator row (TMEM lane) of this thread
+    const bool issuer = (et == 0);       // issues / tracks the bulk stores
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t out_row = smem_u32(out_s) + (uint32_t)row * 128u;
+    const uint32_t aux_row = smem_u32(aux_s) + (uint32_t)row * 128u;
+    float cs0 = 0.f, cs1 = 0.f;          // GELU_BWD: running sums of columns 2*(et&31), +1 over rows (et>>5)*16..+15
+    float bias[(MODE == SCOT_EPI_GELU_BWD) ? 1 : 32];  // bias of this thread's 32 columns, reloaded per column block
+    int bias_cb = -1;
+    int lt = 0;
+    for (int t = t_begin; t < t_end; ++t, ++lt) {
+      const int cb = t / ga.tiles_m;
+      const int m0 = (t - cb * ga.tiles_m) * BM, n0 = cb * ABN;
+      const int buf = lt & 1;
+      if constexpr (MODE != SCOT_EPI_GELU_BWD) {
+        if (cb != bias_cb) {
+          bias_cb = cb;
+          const int cbase = n0 + half * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bias[j] = (ga.bias != nullptr && cbase + j < ga.N) ? __ldg(ga.bias + cbase + j) : 0.f;
+        }
+      }
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+      float v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t)(buf * kAccCols + half * 32) + ((uint32_t)(q * 32) << 16), v);
+      // the previous tile's bulk store must have finished reading the output tile(s) in smem (it had a whole tile time)
+      if (issuer) bulk_wait_read<0>();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[buf]);  // the MMA warp may start the tile after next in this accumulator
+      if constexpr (MODE == SCOT_EPI_GELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // 8 columns = one 16-byte chunk of each output row
+          uint32_t g4[4], a4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float x0 = v[j * 8 + 2 * k] + bias[j * 8 + 2 * k], x1 = v[j * 8 + 2 * k + 1] + bias[j * 8 + 2 * k + 1];
+            float c0, p0, c1, p1;
+            gelu_parts(x0, c0, p0);
+            gelu_parts(x1, c1, p1);
+            g4[k] = pack_bf16x2(fmaf(x0, p0, c0), fmaf(x1, p1, c1));  // gelu'
+            a4[k] = pack_bf16x2(x0 * c0, x1 * c1);                    // gelu
+          }
+          const uint32_t off = (((uint32_t)(half * 4 + j)) ^ swz) << 4;
+          sts128(out_row + off, g4[0], g4[1], g4[2], g4[3]);
+          sts128(out_row + kOutTileBytes + off, a4[0], a4[1], a4[2], a4[3]);
+        }
+      } else if constexpr (MODE == SCOT_EPI_BF16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t o4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            o4[k] = pack_bf16x2(v[j * 8 + 2 * k] + bias[j * 8 + 2 * k], v[j * 8 + 2 * k + 1] + bias[j * 8 + 2 * k + 1]);
+          sts128(out_row + ((((uint32_t)(half * 4 + j)) ^ swz) << 4), o4[0], o4[1], o4[2], o4[3]);
+        }
+      } else {  // GELU_BWD: dh = acc * gelu'(h), gelu'(h) from the aux ring
+        const int as = lt & 1;
+        mbar_wait(&aux_full_bar[as], ((uint32_t)lt >> 1) & 1u);
+        uint4 a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = lds128(aux_row + (uint32_t)(as * kOutTileBytes) + ((((uint32_t)(half * 4 + j)) ^ swz) << 4));
+        mbar_arrive(&aux_empty_bar[as]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t w[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
+          uint32_t o4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 g = unpack_bf16x2(w[k]);
+            o4[k] = pack_bf16x2(v[j * 8 + 2 * k] * g.x, v[j * 8 + 2 * k + 1] * g.y);
+          }
+          sts128(out_row + ((((uint32_t)(half * 4 + j)) ^ swz) << 4), o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+      if (issuer) {
+        if constexpr (MODE == SCOT_EPI_GELU) {
+          if (ga.has_out0) tma_store_2d(&ga.tmOut0, out_s, n0, m0);
+          tma_store_2d(&ga.tmOut1, out_s + kOutTileBytes, n0, m0);
+        } else {
+          tma_store_2d(&ga.tmOut0, out_s, n0, m0);
+        }
+        bulk_commit();
+      }
+      if constexpr (MODE == SCOT_EPI_GELU_BWD) {
+        // bias gradient: column sums of the bf16 values just staged (rows >= M hold zeros: their A rows were zero-filled)
+        const int cp = et & 31, rg = et >> 5;
+        const uint32_t chunk = (uint32_t)(cp >> 2), word = (uint32_t)(cp & 3) * 4;
+        const uint32_t obase = smem_u32(out_s) + word;
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+          const int r = rg * 16 + rr;
+          const float2 f = unpack_bf16x2(lds32(obase + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+          cs0 += f.x;
+          cs1 += f.y;
+        }
+        const bool last_of_col = (t + 1 >= t_end) || ((t + 1) / ga.tiles_m != cb);
+        if (last_of_col && ga.colsum != nullptr) {
+          const int c = n0 + 2 * cp;
+          if (c < ga.N) atomicAdd(ga.colsum + c, cs0);
+          if (c + 1 < ga.N) atomicAdd(ga.colsum + c + 1, cs1);
+          cs0 = cs1 = 0.f;
+        }
+      }
+    }
+    if (issuer) bulk_wait<0>();  // all stores of this CTA are performed before the grid can complete
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// =================================================================================================
 // SIMT reference kernel (bring-up / cross-check path; same epilogue semantics, fp32 FMA on CUDA cores)
 // =================================================================================================
 template <int MODE>
@@ -533,9 +787,84 @@ int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, in
   return launch_tc_group<BN, AMN, BMN, MODE>(&h, 1, stream);
 }
 
+// SCOT_GEMM_ASYNC_EPI=0 falls back to the register/staging epilogue of gemm_tc_kernel for the bf16-output modes (A/B runs)
+bool async_epi_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SCOT_GEMM_ASYNC_EPI");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <int BMN, int MODE>
+int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
+                 cudaStream_t stream) {
+  AsyncArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  int rc = make_tmap(&ga.tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+  if (rc) return rc;
+  if (BMN == 0) rc = make_tmap(&ga.tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, ABN);
+  else rc = make_tmap(&ga.tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
+  if (MODE == SCOT_EPI_GELU) {
+    if (ep.out0 != nullptr) {
+      rc = make_tmap(&ga.tmOut0, ep.out0, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld0, 64, BM);
+      if (rc) return rc;
+    }
+    rc = make_tmap(&ga.tmOut1, ep.out1, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld1, 64, BM);
+    if (rc) return rc;
+  } else {
+    rc = make_tmap(&ga.tmOut0, ep.out0, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld0, 64, BM);
+    if (rc) return rc;
+    ga.tmOut1 = ga.tmOut0;
+  }
+  if (MODE == SCOT_EPI_GELU_BWD) {
+    rc = make_tmap(&ga.tmAux, ep.aux, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldaux, 64, BM);
+    if (rc) return rc;
+  }
+  ga.M = M;
+  ga.N = N;
+  ga.kblocks = ceil_div(K, BK);
+  ga.tiles_m = ceil_div(M, BM);
+  ga.tiles_n = ceil_div(N, ABN);
+  ga.total_tiles = ga.tiles_m * ga.tiles_n;
+  ga.bias = ep.bias;
+  ga.colsum = ep.colsum;
+  ga.has_out0 = ep.out0 != nullptr;
+  const size_t fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + (MODE == SCOT_EPI_GELU_BWD ? 2 * kOutTileBytes : 0) +
+                       (MODE == SCOT_EPI_GELU ? 2 : 1) * kOutTileBytes;
+  const size_t budget = (size_t)(227 * 1024) / 2 - 1024;
+  int stages = (int)((budget - fixed) / kAStageBytes);
+  if (stages > 4) stages = 4;
+  SCOT_REQUIRE(stages >= 2, "gemm(async epilogue): shared memory budget");
+  const size_t smem = fixed + (size_t)stages * kAStageBytes;
+  auto kern = gemm_async_epi_kernel<BMN, MODE>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 / 2));
+    attr_done = true;
+  }
+  const int max_ctas = g_num_sms * 2;
+  const int grid = ga.total_tiles < max_ctas ? ga.total_tiles : max_ctas;
+  SCOT_CHECK_CUDA(scot_launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, ga, stages));
+  SCOT_LAUNCH_CHECK();
+  return 0;
+}
+
+// TMA needs 16-byte aligned bases and row pitches for every tensor it touches
+bool tma_ok(const void* p, long ld) { return p == nullptr || ((((uintptr_t)p) & 15) == 0 && ld % 8 == 0); }
+
 template <int AMN, int BMN, int MODE>
 int dispatch_bn(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
                 cudaStream_t stream) {
+  // bf16-output modes: async-epilogue kernel (TMA stores, TMA-fed auxiliary operand), 128 x 64 tiles, two CTAs per SM
+  if constexpr (AMN == 0 && (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_GELU_BWD || MODE == SCOT_EPI_BF16)) {
+    if (async_epi_enabled() && tma_ok(ep.out0, ep.ld0) && tma_ok(ep.out1, ep.ld1) && tma_ok(ep.aux, ep.ldaux) &&
+        (MODE != SCOT_EPI_GELU || ep.out1 != nullptr) && (MODE != SCOT_EPI_GELU_BWD || ep.aux != nullptr) &&
+        (BMN == 0 || N % 8 == 0))
+      return launch_async<BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+  }
   // epilogue-bound modes (two bf16 streams / transcendental math): 128 x 64 tiles, two resident CTAs per SM
   if constexpr (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_GELU_BWD) {
     if (N % 64 == 0 || N > 64) return launch_tc<64, AMN, BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
