@@ -118,8 +118,8 @@ int scot_cpb_bwd(const ScotCpbTable* table, const float* params, float* grads, v
 /* shifted-window cosine attention (HF:421-487 + scOT/model.py:522-559) on qkv [tokens, 3C] bf16 */
 int scot_attn_fwd(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, int batch, int res, int ws,
                   int shift, int heads, int head_dim, void* stream);
-/* `partial`: fp32 accumulation buffer of scot_attn_bwd_partial_bytes() bytes for the relative-position-bias gradient;
- * it must be ZERO on entry and is zero again on return (the engine clears it once per backward pass). */
+/* `partial` / scot_attn_bwd_partial_bytes(): reserved (kept for ABI stability). The relative-position-bias gradient is
+ * folded onto `dtab` inside the dq kernel; `partial` may be NULL. `dtab` / `dalpha` are accumulated into (+=). */
 size_t scot_attn_bwd_partial_bytes(int ws, int heads, int total_windows);
 int scot_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, const float* tab2, const float* alpha,
                   void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha, float* g_qbias,

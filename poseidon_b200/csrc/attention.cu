@@ -455,6 +455,42 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
   }
 }
 
+// Bias-gradient fold executed at the end of the dq kernel. `sacc` holds, per warp, a 16 x N tile of summed dS in mma
+// fragment order: element (m, n) of m-tile mt lives at  warp(mt) * 16N + (((n>>3)<<2) + reg) * 32 + lane  with
+// lane = (m%8)*4 + (n%8)/2 and reg = ((m%16)/8)*2 + n%2. One thread per table entry (dp, dq) = (p_query - p_key,
+// q_query - q_key) walks the (query, key) pairs with that displacement whose query row belongs to this CTA.
+template <int WS, int NWARP>
+__device__ __forceinline__ void fold_bias_to_table(const float* __restrict__ sacc, float* __restrict__ dtab, int h, int heads,
+                                                   int rg, int tid, int nthreads) {
+  constexpr int N = WS * WS, MT = N / 16, SIDE = 2 * WS - 1, TABN = SIDE * SIDE;
+  constexpr int WPI = (NWARP / MT) > 1 ? (NWARP / MT) : 1;  // windows processed side by side (small windows)
+  constexpr int ACC = 16 * N;
+  const int mt_lo = (MT > NWARP) ? rg * NWARP : 0;            // m-tiles owned by this CTA (row groups exist for WS = 16 only)
+  const int mt_hi = (MT > NWARP) ? mt_lo + NWARP : MT;
+  for (int r = tid; r < TABN; r += nthreads) {
+    const int dp = r / SIDE - (WS - 1), dq = r % SIDE - (WS - 1);
+    int pm0 = dp > 0 ? dp : 0, pm1 = dp < 0 ? WS + dp : WS;
+    const int qm0 = dq > 0 ? dq : 0, qm1 = dq < 0 ? WS + dq : WS;
+    if (MT > NWARP) {  // WS == 16: m-tile index == window row
+      pm0 = pm0 > mt_lo ? pm0 : mt_lo;
+      pm1 = pm1 < mt_hi ? pm1 : mt_hi;
+    }
+    float acc = 0.f;
+    for (int pm = pm0; pm < pm1; ++pm) {
+      for (int qm = qm0; qm < qm1; ++qm) {
+        const int m = pm * WS + qm, n = (pm - dp) * WS + (qm - dq);
+        const int mt = m >> 4;
+        const int lane = ((m & 7) << 2) | ((n & 7) >> 1);
+        const int reg = (((m >> 3) & 1) << 1) | (n & 1);
+        const int slot = (((n >> 3) << 2) + reg) * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < WPI; ++c) acc += sacc[(c * MT + mt - mt_lo) * ACC + slot];
+      }
+    }
+    if (pm1 > pm0) atomicAdd(dtab + r * heads + h, acc);  // dtab is zero at the start of the backward pass
+  }
+}
+
 // =================================================================================================
 // backward, kernel 1: dq (+ relative-position-bias and logit-scale gradients)
 //   CTA = (head, row group, window chunk); every warp owns one 16-query tile and loops over windows;
@@ -481,7 +517,7 @@ template <int WS, int HD, int NWARP, bool SHIFT>
 __global__ void __launch_bounds__(NWARP * 32)
 attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf, const bf16* __restrict__ do_buf,
                    const float* __restrict__ lse, const float* __restrict__ tab2, const float* __restrict__ alpha,
-                   bf16* __restrict__ dqkv, float* __restrict__ dbias_partial, float* __restrict__ dalpha,
+                   bf16* __restrict__ dqkv, float* __restrict__ dtab, float* __restrict__ dalpha,
                    float* __restrict__ g_qbias, WinGeom g, int total_windows, int windows_per_chunk) {
   pdl_launch_dependents();
   pdl_wait();
@@ -650,16 +686,10 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
     }
   }
   __syncthreads();
-  // add this CTA's bias-gradient accumulators into the per-head buffer [head][rg][warp][16*N] (L2 red.add, 16 B
-  // per op): the sum over window chunks happens in the L2 instead of a [chunks][...] dump + second-stage reduction
-  {
-    float* dst = dbias_partial + ((long)h * Cfg::RG + rg) * NWARP * Cfg::ACC_PER_WARP;
-    for (int i = tid * 4; i < NWARP * Cfg::ACC_PER_WARP; i += nthreads * 4) {
-      const float4 v = *reinterpret_cast<const float4*>(sacc + i);
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                   : "memory");
-    }
-  }
+  // fold this CTA's bias-gradient accumulators (fragment order, summed over its windows) onto the (2ws-1)^2 table of
+  // the head through the relative position index (HF:512-523) and add the <= 961 table entries to the layer's
+  // gradient table: a gather per table entry, no N x N round trip through global memory, no second kernel
+  fold_bias_to_table<WS, NWARP>(sacc, dtab, h, g.heads, rg, tid, nthreads);
   acc_alpha = warp_sum(acc_alpha);
   if (lane == 0) atomicAdd(dalpha + h, acc_alpha);
   // query-bias gradient: sum over the 8 row groups of the warp (lanes with equal cq), then one atomic per column
@@ -674,50 +704,6 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
       if (gq == 0 && g_qbias != nullptr) atomicAdd(g_qbias + h * HD + d * 8 + 2 * cq + j, v);
     }
   }
-}
-
-// Folds the accumulated N x N bias gradient of one head onto the (2ws-1)^2 table through the relative position index
-// (HF:512-523). Gather form: one thread per table entry (head, dp, dq) walks the <= ws^2 (query, key) pairs with that
-// displacement, reads them from the fragment-ordered accumulation buffer (and clears them for the next layer): no
-// atomics, deterministic.
-template <int WS, int NWARP>
-__global__ void __launch_bounds__(128)
-attn_bias_reduce_kernel(float* __restrict__ partial, float* __restrict__ dtab, int heads, int chunks) {
-  pdl_launch_dependents();
-  pdl_wait();
-  constexpr int N = WS * WS, MT = N / 16;
-  constexpr int SIDE = 2 * WS - 1, TABN = SIDE * SIDE;
-  constexpr int RGW = (MT >= NWARP) ? MT : NWARP;        // warp slots per head in the accumulation buffer
-  constexpr int COPIES = (MT >= NWARP) ? 1 : NWARP / MT;  // several windows per CTA -> the same tile appears COPIES times
-  constexpr int PER_HEAD = RGW * 16 * N;
-  (void)chunks;
-  // one warp per table entry; lanes split the (query, key) pairs of that displacement
-  const int lane_id = threadIdx.x & 31;
-  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (idx >= TABN * heads) return;
-  const int r = idx / heads, h = idx - r * heads;
-  const int dp = r / SIDE - (WS - 1), dq = r % SIDE - (WS - 1);  // (p_query - p_key, q_query - q_key)
-  float* base = partial + (long)h * PER_HEAD;
-  float acc = 0.f;
-  const int pm_lo = dp > 0 ? dp : 0, np = WS - (dp < 0 ? -dp : dp);
-  const int qm_lo = dq > 0 ? dq : 0, nq = WS - (dq < 0 ? -dq : dq);
-  for (int i = lane_id; i < np * nq; i += 32) {
-    const int pm = pm_lo + i / nq, qm = qm_lo + i % nq;
-    const int m = pm * WS + qm, n = (pm - dp) * WS + (qm - dq);
-    // fragment position of (m, n): tile m/16, lane (m%8)*4 + (n%8)/2, register ((m%16)/8)*2 + n%2, column tile n/8
-    const int mt = m >> 4;
-    const int lane = ((m & 7) << 2) | ((n & 7) >> 1);
-    const int reg = (((m >> 3) & 1) << 1) | (n & 1);
-    const int slot = (((n >> 3) << 2) + reg) * 32 + lane;
-#pragma unroll
-    for (int cpy = 0; cpy < COPIES; ++cpy) {
-      float* src = base + (long)(mt + cpy * MT) * 16 * N + slot;
-      acc += *src;
-      *src = 0.f;
-    }
-  }
-  acc = warp_sum(acc);
-  if (lane_id == 0) atomicAdd(dtab + r * heads + h, acc);  // dtab is zero at the start of the backward pass
 }
 
 // =================================================================================================
@@ -987,8 +973,8 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
   if (chunks < 1) chunks = 1;
   int wpc = ceil_div(iters, chunks) * C1::WPI;
   chunks = ceil_div(total_windows, wpc);
-  const size_t need = (size_t)g.heads * C1::RG * NWARP * C1::ACC_PER_WARP * sizeof(float);
-  SCOT_REQUIRE(need <= partial_bytes, "attention backward: bias partial buffer too small (%zu > %zu)", need, partial_bytes);
+  (void)partial;
+  (void)partial_bytes;
   // dk/dv kernel: ~66 KB of smem -> three CTAs per SM
   int chunks2 = (3 * num_sms()) / (g.heads * C2::KG);
   if (chunks2 > iters) chunks2 = iters;
@@ -997,15 +983,11 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
   chunks2 = ceil_div(total_windows, wpc2);
   dim3 grid1(g.heads, C1::RG, chunks);
   SCOT_CHECK_CUDA(scot_launch_pdl(k1, grid1, dim3(NWARP * 32), C1::smem, st, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
-                                  tab2, alpha, (bf16*)dqkv, partial, dalpha, g_qbias, g, total_windows, wpc));
+                                  tab2, alpha, (bf16*)dqkv, dtab, dalpha, g_qbias, g, total_windows, wpc));
   SCOT_LAUNCH_CHECK();
   dim3 grid2(g.heads, C2::KG, chunks2);
   SCOT_CHECK_CUDA(scot_launch_pdl(k2, grid2, dim3(NWARP * 32), C2::smem, st, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
                                   tab2, alpha, (bf16*)dqkv, g_vbias, g, total_windows, wpc2));
-  SCOT_LAUNCH_CHECK();
-  constexpr int kTab = (2 * WS - 1) * (2 * WS - 1);
-  SCOT_CHECK_CUDA(scot_launch_pdl(attn_bias_reduce_kernel<WS, NWARP>, dim3(ceil_div(kTab * g.heads, 4)), dim3(128), 0, st, partial,
-                                  dtab, g.heads, chunks));
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -1013,13 +995,10 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
 }  // namespace
 
 size_t scot_attn_bwd_partial_bytes(int ws, int heads, int total_windows) {
-  // [head][N x N] fp32 accumulation buffer (RG * NWARP * 16 * N = N * N positions per head, or 8 x 16 x N when several
-  // windows share a CTA). Must be ZERO on entry to scot_attn_bwd; it is zero again on return.
-  (void)total_windows;
-  const int N = ws * ws;
-  const int mt = N / 16;
-  const int per_head = (mt >= 8 ? mt : 8) * 16 * N;
-  return (size_t)heads * per_head * sizeof(float);
+  // The bias gradient is folded onto the table inside the dq kernel: no global scratch is needed any more. The entry
+  // point (and the `partial` argument of scot_attn_bwd) stay for ABI stability; a small non-zero size keeps callers simple.
+  (void)ws; (void)heads; (void)total_windows;
+  return 256;
 }
 
 int scot_cpb_fwd_launch(const ScotCpbTable* tab, const float* params, void* arena, cudaStream_t st) {
@@ -1075,7 +1054,7 @@ int scot_attn_bwd_launch(const void* qkv, const void* o, const void* d_o, const 
                          const float* alpha, void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha,
                          float* g_qbias, float* g_vbias, int batch, int res, int ws, int shift, int heads, int hd,
                          cudaStream_t st) {
-  SCOT_REQUIRE(qkv && o && d_o && lse && tab2 && alpha && dqkv && partial && dtab && dalpha, "attn_bwd: null pointer");
+  SCOT_REQUIRE(qkv && o && d_o && lse && tab2 && alpha && dqkv && dtab && dalpha, "attn_bwd: null pointer");
   WinGeom g{res, shift, res / ws, heads, heads * hd};
   const int tw = batch * g.nws * g.nws;
 #define BWD_ARGS qkv, o, d_o, lse, tab2, alpha, dqkv, partial, partial_bytes, dtab, dalpha, g_qbias, g_vbias, g, tw, st

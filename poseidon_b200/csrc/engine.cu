@@ -712,7 +712,6 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
   const int NR = d.num_out_channels * d.patch_size * d.patch_size;
   const long HW = (long)d.image_size * d.image_size;
   SCOT_CHECK_CUDA(cudaMemsetAsync(c.at<uint8_t>(e->dgrads_zero_begin), 0, e->dgrads_zero_bytes, c.st));
-  SCOT_CHECK_CUDA(cudaMemsetAsync(c.at<uint8_t>(e->partial), 0, e->partial_bytes, c.st));  // bias-gradient accumulator
   // ---- loss + patch recovery backward ----
   float* dpred = c.at<float>(e->dpred);
   RC(scot_loss_bwd_launch(e->last_pred, e->last_labels, c.at<float>(e->loss_sums), grad_loss, grad_pred, e->last_mask,
