@@ -141,7 +141,7 @@ struct ClnBwdArgs {
 };
 
 template <int LPR, int V>
-__global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
+__global__ void __launch_bounds__(256, (V <= 3 ? 2 : 1)) cln_bwd_kernel(ClnBwdArgs p) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float red[];  // [warps][5][C]
@@ -152,15 +152,20 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
   const int nvec = p.C >> 2;
   const long row_begin = (long)blockIdx.x * p.rows_per_block;
 
-  // scale = ab + aw * t(row): the block may span several samples, so t is looked up per row
-  float4 sab[V], saw[V];
+  // scale = ab + aw * t(row): the block may span several samples, so t is looked up per row. Wide rows keep the two
+  // scale vectors in registers; narrow-row variants (several rows per warp, V = 3) re-read them through L1 instead, which
+  // keeps the kernel at two CTAs per SM.
+  constexpr bool kScaleInRegs = (V <= 2);
+  float4 sab[kScaleInRegs ? V : 1], saw[kScaleInRegs ? V : 1];
+  if constexpr (kScaleInRegs) {
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const int cv = sl + i * LPR;
-    sab[i] = saw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cv < nvec) {
-      sab[i] = *reinterpret_cast<const float4*>(p.ab + cv * 4);
-      if (p.aw != nullptr) saw[i] = *reinterpret_cast<const float4*>(p.aw + cv * 4);
+    for (int i = 0; i < V; ++i) {
+      const int cv = sl + i * LPR;
+      sab[i] = saw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cv < nvec) {
+        sab[i] = *reinterpret_cast<const float4*>(p.ab + cv * 4);
+        if (p.aw != nullptr) saw[i] = *reinterpret_cast<const float4*>(p.aw + cv * 4);
+      }
     }
   }
   // column sums: dy*zhat, dy, dz and (conditioned norm) the same two weighted by t
@@ -169,10 +174,11 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
   for (int i = 0; i < V; ++i) acc_a[i] = acc_c[i] = acc_b[i] = acc_at[i] = acc_ct[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // R rows per (sub-)warp are processed together so that several independent global loads are in flight
-  constexpr int R = (V <= 3) ? 4 : (V <= 6 ? 2 : 1);
+  constexpr int R = (V <= 1) ? 4 : (V <= 6 ? 2 : 1);
   const int row_stride = nwarps * RPW;
   for (int rr0 = warp * RPW + sub; rr0 < p.rows_per_block; rr0 += row_stride * R) {
-    float4 dy[R][V], zh[R][V];
+    float4 dy[R][V];
+    uint2 zp[R][V];  // normalised input, packed bf16 (unpacked at each use: two ALU ops instead of two more registers)
     float rs[R], tt[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
@@ -186,12 +192,10 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
         const int cv = sl + i * LPR;
         if (cv < nvec && in) {
           dy[k][i] = *reinterpret_cast<const float4*>(p.dy + r_out * p.C + cv * 4);
-          const uint2 zr = *reinterpret_cast<const uint2*>(p.zhat + r_out * p.C + cv * 4);
-          const float2 z01 = unpack_bf16x2(zr.x), z23 = unpack_bf16x2(zr.y);
-          zh[k][i] = make_float4(z01.x, z01.y, z23.x, z23.y);
+          zp[k][i] = *reinterpret_cast<const uint2*>(p.zhat + r_out * p.C + cv * 4);
         } else {
           dy[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          zh[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          zp[k][i] = make_uint2(0u, 0u);
         }
       }
     }
@@ -200,11 +204,11 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
       const int rr = rr0 + k * row_stride;  // rows beyond the block contribute zeros and are not stored
       const long r_out = row_begin + rr;
       float s1 = 0.f, s2 = 0.f;
+      const float t = tt[k];
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const float4 pz = make_float4(dy[k][i].x * zh[k][i].x, dy[k][i].y * zh[k][i].y, dy[k][i].z * zh[k][i].z,
-                                      dy[k][i].w * zh[k][i].w);
-        const float t = tt[k];
+        const float2 z01 = unpack_bf16x2(zp[k][i].x), z23 = unpack_bf16x2(zp[k][i].y);
+        const float4 pz = make_float4(dy[k][i].x * z01.x, dy[k][i].y * z01.y, dy[k][i].z * z23.x, dy[k][i].w * z23.y);
         acc_a[i].x += pz.x; acc_a[i].y += pz.y; acc_a[i].z += pz.z; acc_a[i].w += pz.w;
         acc_c[i].x += dy[k][i].x; acc_c[i].y += dy[k][i].y; acc_c[i].z += dy[k][i].z; acc_c[i].w += dy[k][i].w;
         acc_at[i].x = fmaf(t, pz.x, acc_at[i].x); acc_at[i].y = fmaf(t, pz.y, acc_at[i].y);
@@ -212,10 +216,22 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
         acc_ct[i].x = fmaf(t, dy[k][i].x, acc_ct[i].x); acc_ct[i].y = fmaf(t, dy[k][i].y, acc_ct[i].y);
         acc_ct[i].z = fmaf(t, dy[k][i].z, acc_ct[i].z); acc_ct[i].w = fmaf(t, dy[k][i].w, acc_ct[i].w);
         // dzhat = dy * scale(t)
-        dy[k][i].x *= fmaf(saw[i].x, t, sab[i].x); dy[k][i].y *= fmaf(saw[i].y, t, sab[i].y);
-        dy[k][i].z *= fmaf(saw[i].z, t, sab[i].z); dy[k][i].w *= fmaf(saw[i].w, t, sab[i].w);
+        float4 b4, w4;
+        if constexpr (kScaleInRegs) {
+          b4 = sab[i];
+          w4 = saw[i];
+        } else {
+          const int cv = sl + i * LPR;
+          b4 = w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cv < nvec) {
+            b4 = __ldg(reinterpret_cast<const float4*>(p.ab + cv * 4));
+            if (p.aw != nullptr) w4 = __ldg(reinterpret_cast<const float4*>(p.aw + cv * 4));
+          }
+        }
+        dy[k][i].x *= fmaf(w4.x, t, b4.x); dy[k][i].y *= fmaf(w4.y, t, b4.y);
+        dy[k][i].z *= fmaf(w4.z, t, b4.z); dy[k][i].w *= fmaf(w4.w, t, b4.w);
         s1 += (dy[k][i].x + dy[k][i].y) + (dy[k][i].z + dy[k][i].w);
-        s2 += (dy[k][i].x * zh[k][i].x + dy[k][i].y * zh[k][i].y) + (dy[k][i].z * zh[k][i].z + dy[k][i].w * zh[k][i].w);
+        s2 += (dy[k][i].x * z01.x + dy[k][i].y * z01.y) + (dy[k][i].z * z23.x + dy[k][i].w * z23.y);
       }
 #pragma unroll
       for (int o = LPR / 2; o > 0; o >>= 1) {
@@ -239,11 +255,12 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(ClnBwdArgs p) {
       for (int i = 0; i < V; ++i) {
         const int cv = sl + i * LPR;
         if (cv < nvec) {
+          const float2 z01 = unpack_bf16x2(zp[k][i].x), z23 = unpack_bf16x2(zp[k][i].y);
           float4 dz;
-          dz.x = (dy[k][i].x - m1 - zh[k][i].x * m2) * rstd;
-          dz.y = (dy[k][i].y - m1 - zh[k][i].y * m2) * rstd;
-          dz.z = (dy[k][i].z - m1 - zh[k][i].z * m2) * rstd;
-          dz.w = (dy[k][i].w - m1 - zh[k][i].w * m2) * rstd;
+          dz.x = (dy[k][i].x - m1 - z01.x * m2) * rstd;
+          dz.y = (dy[k][i].y - m1 - z01.y * m2) * rstd;
+          dz.z = (dy[k][i].z - m1 - z23.x * m2) * rstd;
+          dz.w = (dy[k][i].w - m1 - z23.y * m2) * rstd;
           if (p.dz_is_f32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dz) + r_in * p.C + cv * 4) = dz;
           } else {
@@ -303,9 +320,28 @@ int launch_fwd(const ClnFwdArgs& a, cudaStream_t st) {
   return 0;
 }
 template <int LPR, int V>
-int launch_bwd(const ClnBwdArgs& a, cudaStream_t st) {
-  const long blocks = (a.rows + a.rows_per_block - 1) / a.rows_per_block;
+int launch_bwd(const ClnBwdArgs& a_in, cudaStream_t st) {
+  ClnBwdArgs a = a_in;
   const int warps = a.C > 768 ? 4 : 8;  // [warps][5][C] floats of smem must fit 227 KB (C = 1536: Poseidon-L stage 3)
+  if (a.rows_per_block <= 0) {
+    // A block sweeps a contiguous range of rows (it may span samples). Large problems: one wave of resident CTAs
+    // (two per SM for the narrow variants), so that no second, partially filled wave exists and the per-block column
+    // reduction + 5 atomics per column happen once per resident CTA. Small problems: at least 32 rows per block.
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    const long target = (long)sms * (V <= 3 ? 2 : 1);
+    const long unit = (long)warps * (32 / LPR);  // rows per sweep of the block's (sub-)warps
+    long rpb = (a.rows + target - 1) / target;
+    rpb = (rpb + unit - 1) / unit * unit;
+    if (rpb < 32) rpb = 32;
+    a.rows_per_block = (int)rpb;
+  }
+  const long blocks = (a.rows + a.rows_per_block - 1) / a.rows_per_block;
   const size_t smem = (size_t)warps * 5 * a.C * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
@@ -324,6 +360,10 @@ int launch_bwd(const ClnBwdArgs& a, cudaStream_t st) {
 #define CLN_DISPATCH(FN, ARGS)                                                     \
   do {                                                                             \
     const int nvec = (ARGS).C / 4;                                                 \
+    /* narrow rows: several rows per warp (LPR lanes per row, 3 float4 per lane) */ \
+    if (nvec == 12) return FN<4, 3>(ARGS, st);                                     \
+    if (nvec == 24) return FN<8, 3>(ARGS, st);                                     \
+    if (nvec == 48) return FN<16, 3>(ARGS, st);                                    \
     if (nvec <= 8) return FN<8, 1>(ARGS, st);                                      \
     if (nvec <= 16) return FN<16, 1>(ARGS, st);                                    \
     if (nvec <= 32) return FN<32, 1>(ARGS, st);                                    \
@@ -354,13 +394,9 @@ int scot_cln_bwd_launch(const float* dy, const void* zhat, const float* rstd, co
   SCOT_REQUIRE(C % 4 == 0 && rows > 0, "cln_bwd: bad shape");
   SCOT_REQUIRE((aw == nullptr) == (g_aw == nullptr) && (g_aw == nullptr) == (g_cw == nullptr), "cln_bwd: aw/g_aw/g_cw mismatch");
   SCOT_REQUIRE(aw == nullptr || time != nullptr, "cln_bwd: conditioned norm needs time");
-  // a block sweeps a contiguous range of rows (it may span samples): about two blocks per SM keep the per-block
-  // reduction + 5 atomics per column rare while every warp still has several rows in flight
-  // rows per block: enough blocks to fill the machine several times over (every warp keeps R rows in flight), but at
-  // least 32 rows so that the per-block column reduction + 5 atomics per column stay a small fraction
-  long rpb = rows >= 16384 ? 128 : 32;  // measured on B200 (scripts/cln_bwd_sweep.py): larger blocks only add latency
+  long rpb = 0;  // 0: sized by launch_bwd (one resident wave); SCOT_CLN_RPB=<rows per block> overrides (tuning knob)
   {
-    static long override_rpb = -1;  // tuning knob: SCOT_CLN_RPB=<rows per block>
+    static long override_rpb = -1;
     if (override_rpb < 0) {
       const char* e = getenv("SCOT_CLN_RPB");
       override_rpb = e ? atol(e) : 0;
