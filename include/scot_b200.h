@@ -159,6 +159,19 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
  * grad_loss: device scalar or NULL; grad_pred: [B,Cout,H,W] or NULL. Gradients are accumulated, never zeroed. */
 int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void* arena, const float* grad_loss,
                          const float* grad_pred, int gemm_impl, void* stream);
+/* ---- fused optimizer step on the flat buffers (replaces accelerate clip_grad_norm_ + torch.optim.AdamW,
+ * scOT/train.py:286, scOT/trainer.py:295-445) ----------------------------------------------------------------------
+ * out[0] = sum(grads^2) (cleared first). */
+int scot_grad_sq_norm(const float* grads, long n_elems, float* out, void* stream);
+/* AdamW (decoupled weight decay, bias correction; torch.optim.AdamW semantics) over the whole flat buffer.
+ * chunk_group[i/64] = parameter group of elements [64*(i/64), +64) or 255 (padding / frozen: untouched).
+ * group_hp[g*8 ..] = {lr, weight_decay, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), 0} (device memory, so that a
+ * captured CUDA graph follows a learning-rate schedule). grad_sq_norm (nullable) + max_norm > 0: gradients are scaled
+ * by min(1, max_norm / (sqrt(grad_sq_norm)*grad_scale + 1e-6)) on the fly (clip_grad_norm_); grad_scale multiplies every
+ * gradient first (1/world_size after a summed all-reduce). params_bf16 (nullable): bf16 copy refreshed in the same pass. */
+int scot_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16,
+                    const uint8_t* chunk_group, long n_elems, const float* group_hp, int n_groups, const float* grad_sq_norm,
+                    float max_norm, float grad_scale, void* stream);
 /* Re-binds the tensors the next scot_engine_backward reads (the inputs / prediction of a forward that was replayed
  * from a CUDA graph, where the host-side bookkeeping of scot_engine_forward did not run). Host-only, no launch. */
 int scot_engine_bind_io(ScotEngine* e, const float* pixel_values, const float* time, const float* labels,

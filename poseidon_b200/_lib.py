@@ -150,6 +150,10 @@ def _declare_engine(lib):
     lib.scot_engine_backward.restype = i
     lib.scot_engine_bind_io.argtypes = [vp] * 5 + [i, vp]
     lib.scot_engine_bind_io.restype = i
+    lib.scot_grad_sq_norm.argtypes = [vp, l, vp, vp]
+    lib.scot_grad_sq_norm.restype = i
+    lib.scot_adamw_step.argtypes = [vp] * 6 + [l, vp, i, vp, f, f, vp]
+    lib.scot_adamw_step.restype = i
 
 
 _declare_base = _declare

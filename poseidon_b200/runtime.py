@@ -24,7 +24,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model: ScOT, batch: int, device: Optional[torch.device] = None, use_mask: bool = False,
-                 use_graph: bool = True, world_size: int = 1, average: bool = True):
+                 use_graph: bool = True, world_size: int = 1, average: bool = True, optimizer=None):
         cfg = model.config
         self.model = model
         self.device = device or next(model.parameters()).device
@@ -44,6 +44,7 @@ class GraphedTrainStep:
         # d(loss)/d(loss): pre-scaled by 1/world so that the summed all-reduce yields the DDP mean
         self.gscale = torch.full((1,), (1.0 / world_size) if average else 1.0, device=self.device)
         self.graph = None
+        self.optimizer = optimizer  # e.g. poseidon_b200.optim.FlatAdamW: fused clip + AdamW on the flat buffers
         self._impl = model.gemm_impl
         # bind .grad to the flat views once; the graph zeroes and refills the same memory every step
         for p, gv in zip(st["plist"], st["gviews"]):
@@ -89,9 +90,114 @@ class GraphedTrainStep:
         if self.world_size > 1:
             torch.distributed.all_reduce(self.st["gflat"])
 
+    def optimizer_step(self):
+        """clip_grad_norm_ + AdamW on the flat buffers (two launches), after the gradient all-reduce."""
+        if self.optimizer is not None:
+            self.optimizer.step()
+
+    def train_step(self):
+        """graph replay (zero grads, forward, backward) -> one all-reduce -> fused optimizer step"""
+        self.run()
+        self.allreduce()
+        self.optimizer_step()
+
     def launches_per_step(self) -> int:
         lib = _lib.load()
         before = lib.scot_launch_count()
         self._body()
         torch.cuda.synchronize(self.device)
         return int(lib.scot_launch_count() - before)
+
+
+class ARRollout:
+    """Autoregressive rollout on the device (reference scOT/trainer.py:452-603 `_model_forward`
+    with `ar_steps`, scOT/inference.py:210-235): the prediction is fed back as the next input — extra input channels
+    (num_channels > num_out_channels) are carried over (trainer.py:488-501) — with the lead time divided by the
+    number of steps (int `ar_steps`, :459) or multiplied per step (list `ar_steps`, :528-534).
+
+    One CUDA graph holds `engine.forward` + the feedback copy; a rollout is `n` replays on one stream: no host
+    synchronisation, no allocation and no Python-side tensor work between the steps.
+    """
+
+    def __init__(self, model: ScOT, batch: int, device: Optional[torch.device] = None, with_labels: bool = False,
+                 mask_shape=None, use_graph: bool = True):
+        cfg = model.config
+        if not cfg.use_conditioning:
+            raise ValueError("autoregressive rollouts need a time-conditioned model (reference trainer.py:453)")
+        self.model = model
+        self.device = device or next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("ARRollout needs a CUDA device (no CPU fallback)")
+        self.batch = batch
+        self.st = model._ensure_state(self.device, batch)
+        s = cfg.image_size
+        self.cin, self.cout = cfg.num_channels, cfg.num_out_channels
+        if self.cout > self.cin:
+            raise ValueError("rollout needs num_out_channels <= num_channels")
+        self.x = torch.zeros(batch, self.cin, s, s, device=self.device)
+        self.t = torch.zeros(batch, device=self.device)
+        self.y = torch.zeros(batch, self.cout, s, s, device=self.device) if with_labels else None
+        self.mask, self.mask_mode = None, 0
+        if mask_shape is not None:
+            if not with_labels:
+                raise ValueError("pixel_mask needs labels")
+            self.mask = torch.zeros(tuple(mask_shape), dtype=torch.uint8, device=self.device)
+            self.mask_mode = 1 if len(mask_shape) == 2 else 2
+        self.pred = torch.empty(batch, self.cout, s, s, device=self.device)
+        self.loss = torch.zeros(1, device=self.device) if with_labels else None
+        self.graph = None
+        self._impl = model.gemm_impl
+        if use_graph:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._body()  # warm-up outside capture
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+
+    def _body(self):
+        st = self.st
+        st["engine"].forward(st["flat"], st["arena"], self.x, self.t, self.y, self.mask, self.mask_mode, self.pred, self.loss,
+                             self._impl)
+        # feedback: the prediction replaces the first num_out_channels input channels, the rest is carried over
+        self.x[:, :self.cout].copy_(self.pred)
+
+    @torch.no_grad()
+    def run(self, pixel_values, time, ar_steps, labels=None, pixel_mask=None, output_all_steps: bool = False):
+        """Returns (output, loss): output [B, Cout, H, W] of the last step, or [B, steps, Cout, H, W] with
+        `output_all_steps`; loss = mean over the steps (or the per-step stack), None without labels."""
+        if isinstance(ar_steps, int):
+            factors = [1.0 / ar_steps] * ar_steps
+        else:
+            factors = [float(i) for i in ar_steps]
+        self.x.copy_(pixel_values, non_blocking=True)
+        lead = time.to(device=self.device, dtype=torch.float32).reshape(-1)
+        if (labels is not None) != (self.y is not None):
+            raise ValueError("ARRollout was built with_labels=%s" % (self.y is not None))
+        if labels is not None:
+            self.y.copy_(labels, non_blocking=True)
+        if self.mask is not None:
+            if pixel_mask is None:
+                raise ValueError("ARRollout was built with a pixel mask")
+            self.mask.copy_(pixel_mask.to(torch.uint8), non_blocking=True)
+        outs, losses = [], []
+        for f in factors:
+            torch.mul(lead, f, out=self.t)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._body()
+            if output_all_steps:
+                outs.append(self.pred.clone())
+            if self.loss is not None:
+                losses.append(self.loss.clone())
+        if output_all_steps:
+            output = torch.stack(outs, dim=1)
+            loss = torch.stack(losses, dim=0).reshape(-1) if losses else None
+        else:
+            output = self.pred.clone()
+            loss = (torch.stack(losses).sum() / len(factors)) if losses else None
+        return output, loss
