@@ -75,9 +75,14 @@ __device__ __forceinline__ int bias_rowbase(int m) {
   return (m / WS) * (2 * WS - 1) + (m % WS) + (WS - 1) * (2 * WS - 1) + (WS - 1);
 }
 template <int WS>
-__device__ __forceinline__ int bias_coloff(int n) {
+__host__ __device__ constexpr int bias_coloff(int n) {
   return (n / WS) * (2 * WS - 1) + (n % WS);
 }
+// bias_coloff is additive over the index decomposition used by the mma fragments,
+//   n = chunk * KC + nt * 8 + 2 * cq + j   (KC a multiple of WS or a single chunk; 2*cq + j < 8 never carries),
+// so a table lookup tab[rowbase(m) - coloff(n)] becomes ONE per-thread base pointer (rowbase(m0) - coloff(2*cq)),
+// a per-chunk pointer bump (coloff(KC)) and compile-time immediates (coloff(nt*8) + j; + coloff(8) for row m0 + 8):
+// no integer arithmetic per score element.
 
 // ---- cooperative loads --------------------------------------------------------------------------------
 // copy `nrows` token rows x HD bf16 from a [tokens, ld] buffer (column offset col0) into smem [nrows][HD+8]
@@ -360,7 +365,8 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
     const float* utab = stab + u * Cfg::TABN;
     const float a2 = alpha[h] * kLog2e;
     const int m0 = mt * 16 + gq, m1 = m0 + 8;
-    const int rb0 = bias_rowbase<WS>(m0), rb1 = bias_rowbase<WS>(m1);
+    constexpr int RBD = bias_coloff<WS>(8);  // rowbase(m0 + 8) - rowbase(m0)
+    const float* tb = utab + bias_rowbase<WS>(m0) - bias_coloff<WS>(2 * cq);
     const int wf = win_flags(g, bw);
     const int code0 = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, m0), code1 = mask_code<WS>(wf, SHIFT ? WS / 2 : 0, m1);
 
@@ -380,14 +386,15 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
       MaskTerms16 mterm = {0.f, 0.f, 0.f, 0.f};
       if constexpr (SHIFT && WS == 16) mterm = mask_terms16(wf, code0, code1, kc);
       float cm0 = -INFINITY, cm1 = -INFINITY;
+      const float* tk = tb - kc * bias_coloff<WS>(KC);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int n = kc * KC + nt * 8 + 2 * cq + j;
-          const int co = bias_coloff<WS>(n);
-          float v0 = fmaf(s[nt][j], a2, utab[rb0 - co]);
-          float v1 = fmaf(s[nt][2 + j], a2, utab[rb1 - co]);
+          (void)n;
+          float v0 = fmaf(s[nt][j], a2, tk[-(bias_coloff<WS>(nt * 8) + j)]);
+          float v1 = fmaf(s[nt][2 + j], a2, tk[RBD - (bias_coloff<WS>(nt * 8) + j)]);
           if constexpr (SHIFT && WS == 16) {
             v0 += (nt & 1) ? mterm.r0_odd : mterm.r0_even;
             v1 += (nt & 1) ? mterm.r1_odd : mterm.r1_even;
@@ -547,7 +554,8 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
   bf16* myo = mydo + 16 * ROWB;
   float* myacc = sacc + warp * Cfg::ACC_PER_WARP;
   const int m0 = mt * 16 + gq, m1 = m0 + 8;
-  const int rb0 = bias_rowbase<WS>(m0), rb1 = bias_rowbase<WS>(m1);
+  constexpr int RBD = bias_coloff<WS>(8);  // rowbase(m0 + 8) - rowbase(m0)
+  const float* tb = stab + bias_rowbase<WS>(m0) - bias_coloff<WS>(2 * cq);
   float acc_alpha = 0.f;
   float qb_acc[HD / 8][2];
 #pragma unroll
@@ -622,15 +630,16 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
       if constexpr (SHIFT && WS == 16) mterm = mask_terms16(wf, code0, code1, kc);
       uint32_t dsa[NT / 2][4];
       float* accp = myacc + (kc * NT) * 128 + lane;
+      const float* tk = tb - kc * bias_coloff<WS>(KC);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         float ds[4];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int n = kc * KC + nt * 8 + 2 * cq + j;
-          const int co = bias_coloff<WS>(n);
-          float v0 = fmaf(s[nt][j], a2, stab[rb0 - co]);
-          float v1 = fmaf(s[nt][2 + j], a2, stab[rb1 - co]);
+          (void)n;
+          float v0 = fmaf(s[nt][j], a2, tk[-(bias_coloff<WS>(nt * 8) + j)]);
+          float v1 = fmaf(s[nt][2 + j], a2, tk[RBD - (bias_coloff<WS>(nt * 8) + j)]);
           if constexpr (SHIFT && WS == 16) {
             v0 += (nt & 1) ? mterm.r0_odd : mterm.r0_even;
             v1 += (nt & 1) ? mterm.r1_odd : mterm.r1_even;
@@ -642,17 +651,15 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
           const float p0 = fast_exp2(v0 - L0), p1 = fast_exp2(v1 - L1);
           ds[j] = p0 * (dp[nt][j] - D0);
           ds[2 + j] = p1 * (dp[nt][2 + j] - D1);
-          acc_alpha = fmaf(ds[j], s[nt][j], acc_alpha);
-          acc_alpha = fmaf(ds[2 + j], s[nt][2 + j], acc_alpha);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) accp[(nt * 4 + r) * 32] += ds[r];
-        dsa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(ds[0] * al, ds[1] * al);
-        dsa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(ds[2] * al, ds[3] * al);
+        dsa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(ds[0], ds[1]);
+        dsa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
       }
-      mma_p_b<HD, NT / 2>(dq, dsa, uk, kc * KC, lane);  // dq_hat += (alpha dS) k_hat
+      mma_p_b<HD, NT / 2>(dq, dsa, uk, kc * KC, lane);  // dq_raw += dS k_hat   (alpha is applied once, after the loop)
     }
-    // dq = (dq_hat - q_hat (q_hat . dq_hat)) / max(|q|, eps)
+    // dq = (dq_hat - q_hat (q_hat . dq_hat)) / max(|q|, eps), dq_hat = alpha dq_raw
     float dot0 = 0.f, dot1 = 0.f;
     float qh[HD / 8][4];
 #pragma unroll
@@ -662,9 +669,14 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
       qh[d][0] = a.x; qh[d][1] = a.y; qh[d][2] = b.x; qh[d][3] = b.y;
       dot0 += a.x * dq[d][0] + a.y * dq[d][1];
       dot1 += b.x * dq[d][2] + b.y * dq[d][3];
+      dq[d][0] *= al; dq[d][1] *= al; dq[d][2] *= al; dq[d][3] *= al;
     }
     dot0 += __shfl_xor_sync(0xffffffffu, dot0, 1); dot0 += __shfl_xor_sync(0xffffffffu, dot0, 2);
     dot1 += __shfl_xor_sync(0xffffffffu, dot1, 1); dot1 += __shfl_xor_sync(0xffffffffu, dot1, 2);
+    // logit-scale gradient: sum_n dS[m, n] (q_hat[m] . k_hat[n]) = q_hat[m] . dq_raw[m]  (every quad lane holds the row total)
+    if (cq == 0) acc_alpha += dot0 + dot1;
+    dot0 *= al;
+    dot1 *= al;
     const float in0 = sinv[warp * 16 + gq], in1 = sinv[warp * 16 + gq + 8];
     __syncwarp();
 #pragma unroll
@@ -755,7 +767,9 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
   bf16* myk = srow + warp * 2 * 16 * ROWB;
   bf16* myv = myk + 16 * ROWB;
   const int n0 = kt * 16 + gq, n1 = n0 + 8;  // keys owned by this thread's fragment rows
-  const int co0 = bias_coloff<WS>(n0), co1 = bias_coloff<WS>(n1);
+  constexpr int RBD = bias_coloff<WS>(8);  // coloff(n0 + 8) - coloff(n0)
+  // tab[rowbase(m) - coloff(n0)] with m = chunk * QC + nt * 8 + 2 * cq + j: base pointer + immediates (see bias_coloff)
+  const float* tb = stab + bias_rowbase<WS>(0) - bias_coloff<WS>(n0) + bias_coloff<WS>(2 * cq);
   float vb_acc[HD / 8][2];
 #pragma unroll
   for (int d = 0; d < HD / 8; ++d) vb_acc[d][0] = vb_acc[d][1] = 0.f;
@@ -835,16 +849,16 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
       MaskTerms16 mterm = {0.f, 0.f, 0.f, 0.f};
       if constexpr (SHIFT && WS == 16) mterm = mask_terms16(wf, code0, code1, qc);
       uint32_t pta[NT / 2][4], dsta[NT / 2][4];
+      const float* tk = tb + qc * bias_coloff<WS>(QC);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         float p[4], ds[4];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int m = qc * QC + nt * 8 + 2 * cq + j;  // query index (column)
-          const int rb = bias_rowbase<WS>(m);
           const float Lm = ulse[m], Dm = uD[m];
-          float v0 = fmaf(st[nt][j], a2, stab[rb - co0]);
-          float v1 = fmaf(st[nt][2 + j], a2, stab[rb - co1]);
+          float v0 = fmaf(st[nt][j], a2, tk[bias_coloff<WS>(nt * 8) + j]);
+          float v1 = fmaf(st[nt][2 + j], a2, tk[bias_coloff<WS>(nt * 8) + j - RBD]);
           if constexpr (SHIFT && WS == 16) {
             v0 += (nt & 1) ? mterm.r0_odd : mterm.r0_even;
             v1 += (nt & 1) ? mterm.r1_odd : mterm.r1_even;
@@ -855,8 +869,8 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
           }
           p[j] = fast_exp2(v0 - Lm);
           p[2 + j] = fast_exp2(v1 - Lm);
-          ds[j] = p[j] * (dpt[nt][j] - Dm) * al;
-          ds[2 + j] = p[2 + j] * (dpt[nt][2 + j] - Dm) * al;
+          ds[j] = p[j] * (dpt[nt][j] - Dm);
+          ds[2 + j] = p[2 + j] * (dpt[nt][2 + j] - Dm);
         }
         pta[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p[0], p[1]);
         pta[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p[2], p[3]);
@@ -864,7 +878,11 @@ attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf
         dsta[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
       }
       mma_p_b<HD, NT / 2>(dv, pta, udo, qc * QC, lane);   // dV  += P^T dO
-      mma_p_b<HD, NT / 2>(dk, dsta, uq, qc * QC, lane);   // dk_hat += alpha dS^T q_hat
+      mma_p_b<HD, NT / 2>(dk, dsta, uq, qc * QC, lane);   // dk_raw += dS^T q_hat   (alpha is applied once, below)
+    }
+#pragma unroll
+    for (int d = 0; d < HD / 8; ++d) {
+      dk[d][0] *= al; dk[d][1] *= al; dk[d][2] *= al; dk[d][3] *= al;
     }
     // dk = (dk_hat - k_hat (k_hat . dk_hat)) / max(|k|, eps); stage dk in my k rows, dv in my v rows
     float dot0 = 0.f, dot1 = 0.f;
