@@ -334,11 +334,22 @@ int launch_bwd(const ClnBwdArgs& a_in, cudaStream_t st) {
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (sms <= 0) sms = 148;
     }
-    const long target = (long)sms * (V <= 3 ? 2 : 1);
+    static long waves = -1;  // tuning knob: SCOT_CLN_WAVES = blocks per SM the row range is cut into
+    if (waves < 0) {
+      const char* e = getenv("SCOT_CLN_WAVES");
+      waves = e ? atol(e) : 0;
+    }
+    const long target = (long)sms * (waves > 0 ? waves : (V <= 3 ? 2 : 1));
     const long unit = (long)warps * (32 / LPR);  // rows per sweep of the block's (sub-)warps
     long rpb = (a.rows + target - 1) / target;
     rpb = (rpb + unit - 1) / unit * unit;
-    if (rpb < 32) rpb = 32;
+    static long min_rpb = -1;  // tuning knob: SCOT_CLN_MIN_RPB
+    if (min_rpb < 0) {
+      const char* e = getenv("SCOT_CLN_MIN_RPB");
+      min_rpb = e ? atol(e) : 8;  // measured on B200: 8 rows (one per warp) beat 16 / 32 / 64 at the deep stages
+      if (min_rpb < 1) min_rpb = 8;
+    }
+    if (rpb < min_rpb) rpb = (min_rpb + unit - 1) / unit * unit;
     a.rows_per_block = (int)rpb;
   }
   const long blocks = (a.rows + a.rows_per_block - 1) / a.rows_per_block;
