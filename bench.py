@@ -271,16 +271,19 @@ def main():
     for p in model.parameters():
         p.grad = None
 
-    dx, dy, dt = (torch.empty_like(hx, device=dev), torch.empty_like(hy, device=dev), torch.empty_like(ht, device=dev))
+    from poseidon_b200.runtime import DevicePrefetcher
+
+    def host_batches():
+        while True:  # the data loader: every step's batch sits in pinned host memory
+            yield {"pixel_values": hx, "labels": hy, "time": ht}
+
+    # double-buffered H2D: the copy of step i+1 is issued (on a side stream) inside step i's timed region
+    feed = DevicePrefetcher(host_batches(), dev)
 
     def e2e_step():
-        # host (pinned) -> device copies of this step's batch into the loader's device buffers
-        dx.copy_(hx, non_blocking=True)
-        dy.copy_(hy, non_blocking=True)
-        dt.copy_(ht, non_blocking=True)
-        x, y, t = dx, dy, dt
+        batch = next(feed)  # issues the H2D copies of the next batch, waits (on the GPU) for this one
         model.flat_gradients.zero_()
-        out = model(pixel_values=x, time=t, labels=y)
+        out = model(pixel_values=batch["pixel_values"], time=batch["time"], labels=batch["labels"])
         out.loss.backward()
         if world > 1:
             torch.distributed.all_reduce(model.flat_gradients)
@@ -295,11 +298,25 @@ def main():
         last_loss = e2e_step()
     barrier()
     e2e_ms = (time.perf_counter() - t0) / n_e2e * 1e3
+    # ---- informational: the same step followed by the fused optimizer (grad-norm clip + AdamW on the flat buffers)
+    from poseidon_b200.optim import FlatAdamW, build_param_groups
+    opt = FlatAdamW(build_param_groups(model, 0.01), model, lr=1e-6, max_grad_norm=5.0)
+    step.optimizer = opt
+    for _ in range(3):
+        step.train_step()
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    for _ in range(max(3, args.steps // 2)):
+        step.train_step()
+    o1.record()
+    barrier()
+    opt_ms = o0.elapsed_time(o1) / max(3, args.steps // 2)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
-        tt = torch.tensor([ms, e2e_ms], device=dev)
+        tt = torch.tensor([ms, e2e_ms, opt_ms], device=dev)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-        ms, e2e_ms = float(tt[0]), float(tt[1])
+        ms, e2e_ms, opt_ms = float(tt[0]), float(tt[1]), float(tt[2])
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -359,12 +376,15 @@ def main():
                 "h2d_bytes_per_step": int((hx.numel() + hy.numel() + ht.numel()) * 4), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms},
         "gpu_launches": launches * args.steps,
+        # fwd+bwd + one all-reduce + fused clip/AdamW (FlatAdamW), device-resident inputs: the full training step
+        "train_step_with_optimizer": {"ms_per_step": opt_ms, "samples_per_s": total_samples / (opt_ms * 1e-3)},
         "clocks": clocks,
-        # dominant kernel: gemm_tc_kernel<64, K-major, K-major, GELU> at the stage-0 MLP shape, HBM bound
+        # dominant kernel: the tcgen05 GEMM with the fused GELU epilogue (async-epilogue variant) at the stage-0 MLP shape, HBM bound
         "roofline": {"bound": "hbm", "achieved": kern_bytes / (kern_us * 1e-6) / 1e9, "peak": peak_hbm, "unit": "GB/s",
                      "frac": kern_bytes / (kern_us * 1e-6) / 1e9 / peak_hbm,
-                     # dram__bytes_read+write of this launch from profiles/r01_ncu_full_summary.md (L2 keeps part of the output)
-                     "traffic": 55.6e6, "kernel": f"gemm_tc_kernel<64,K,K,GELU> M={Mk} N={Nk} K={Kk}", "us_per_launch": kern_us,
+                     # dram__bytes_read+write of this launch from profiles/r01_ncu_full_summary.md (ncu --set full; the
+                     # 126 MB L2 still holds part of the 100 MB of output when the kernel ends)
+                     "traffic": 55.05e6, "kernel": f"gemm_async_epi_kernel<K-major,GELU> M={Mk} N={Nk} K={Kk}", "us_per_launch": kern_us,
                      "algorithmic_bytes": kern_bytes, "peak_source": hbm_src},
         # whole-step tensor roofline (the BASELINE metric): algorithmic fwd+bwd FLOPs / step time vs measured cuBLAS peak
         "step_tensor_roofline": {"achieved_tflops": achieved_tf, "peak_tflops": peak_tf, "frac": achieved_tf / peak_tf,
