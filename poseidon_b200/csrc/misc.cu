@@ -106,18 +106,25 @@ __global__ void scale_add_fwd_kernel(const float* __restrict__ in, const float* 
       make_float4(fmaf(gm.x, zz.x, a.x), fmaf(gm.y, zz.y, a.y), fmaf(gm.z, zz.z, a.z), fmaf(gm.w, zz.w, a.w));
   reinterpret_cast<uint2*>(zb)[i] = make_uint2(pack_bf16x2(zz.x, zz.y), pack_bf16x2(zz.z, zz.w));
 }
-// dz = gamma * g (bf16); g_gamma[c] += sum_m g*z ; g_bias[c] += sum_m dz. One block = 64 rows.
+// dz = gamma * g (bf16); g_gamma[c] += sum_m g*z ; g_bias[c] += sum_m dz.
+// A block sweeps `rows_per_block` rows; thread = (row phase, 4 channels) with every thread active for any C (256 / (C/4)
+// rows per pass), column sums in registers, one smem fold + 8 atomics per column quad and block.
 __global__ void __launch_bounds__(256)
 scale_add_bwd_kernel(const float* __restrict__ g, const bf16* __restrict__ zb, const float* __restrict__ gamma,
-                     bf16* __restrict__ dz, float* __restrict__ g_gamma, float* __restrict__ g_bias, long rows, int C) {
+                     bf16* __restrict__ dz, float* __restrict__ g_gamma, float* __restrict__ g_bias, long rows, int C,
+                     int rows_per_block) {
+  extern __shared__ float4 sab_red[];  // [rpp][c4n][2]
   const int c4n = C / 4;
-  const long row0 = (long)blockIdx.x * 64;
-  for (int c4 = threadIdx.x % 64; c4 < c4n; c4 += 64) {
+  const int rpp = 256 / c4n;  // rows per pass
+  const int c4 = threadIdx.x % c4n, rsub = threadIdx.x / c4n;
+  const bool active = rsub < rpp;
+  const long row0 = (long)blockIdx.x * rows_per_block;
+  const long row1 = row0 + rows_per_block < rows ? row0 + rows_per_block : rows;
+  float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sb = sg;
+  if (active) {
     const float4 gm = *reinterpret_cast<const float4*>(gamma + c4 * 4);
-    float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sb = sg;
-    for (int r = threadIdx.x / 64; r < 64; r += 4) {
-      const long row = row0 + r;
-      if (row >= rows) break;
+#pragma unroll 4
+    for (long row = row0 + rsub; row < row1; row += rpp) {
       const float4 gv = *reinterpret_cast<const float4*>(g + row * C + c4 * 4);
       const uint2 zr = *reinterpret_cast<const uint2*>(zb + row * C + c4 * 4);
       const float2 z01 = unpack_bf16x2(zr.x), z23 = unpack_bf16x2(zr.y);
@@ -127,10 +134,22 @@ scale_add_bwd_kernel(const float* __restrict__ g, const bf16* __restrict__ zb, c
       const float2 d01 = unpack_bf16x2(o.x), d23 = unpack_bf16x2(o.y);
       sb.x += d01.x; sb.y += d01.y; sb.z += d23.x; sb.w += d23.y;
     }
-    atomicAdd(g_gamma + c4 * 4 + 0, sg.x); atomicAdd(g_gamma + c4 * 4 + 1, sg.y);
-    atomicAdd(g_gamma + c4 * 4 + 2, sg.z); atomicAdd(g_gamma + c4 * 4 + 3, sg.w);
-    atomicAdd(g_bias + c4 * 4 + 0, sb.x); atomicAdd(g_bias + c4 * 4 + 1, sb.y);
-    atomicAdd(g_bias + c4 * 4 + 2, sb.z); atomicAdd(g_bias + c4 * 4 + 3, sb.w);
+    sab_red[(rsub * c4n + c4) * 2 + 0] = sg;
+    sab_red[(rsub * c4n + c4) * 2 + 1] = sb;
+  }
+  __syncthreads();
+  if (threadIdx.x < c4n) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bsum = a;
+    for (int r = 0; r < rpp; ++r) {
+      const float4 u = sab_red[(r * c4n + threadIdx.x) * 2 + 0], v = sab_red[(r * c4n + threadIdx.x) * 2 + 1];
+      a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+      bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+    }
+    const int c = threadIdx.x * 4;
+    atomicAdd(g_gamma + c + 0, a.x); atomicAdd(g_gamma + c + 1, a.y);
+    atomicAdd(g_gamma + c + 2, a.z); atomicAdd(g_gamma + c + 3, a.w);
+    atomicAdd(g_bias + c + 0, bsum.x); atomicAdd(g_bias + c + 1, bsum.y);
+    atomicAdd(g_bias + c + 2, bsum.z); atomicAdd(g_bias + c + 3, bsum.w);
   }
 }
 
@@ -370,20 +389,27 @@ conv5_tiled_kernel(const float* __restrict__ in, const float* __restrict__ w, co
     }
   }
 }
-// g_w[o,ic,dy,dx] += sum_{b,y,x} dpred[b,o,y,x] * P[b,ic,y+dy-2,x+dx-2]; one thread per weight, tiles in smem
-constexpr int C5W_TW = 32, C5W_TH = 16;  // smaller tile for the weight gradient (two tiles in smem)
+// g_w[o,ic,dy,dx] += sum_{b,y,x} dpred[b,o,y,x] * P[b,ic,y+dy-2,x+dx-2].
+// Thread = (o, ic, tile row y): it keeps all 25 taps of its (o, ic) pair in registers and slides a 5 x 5 register window
+// of P along x, so one tile column costs 6 shared loads for 25 FMAs (the one-thread-per-weight form needs 50). The 16
+// row-threads of a pair sit in one half-warp: a shuffle tree folds them, lane 0 issues the 25 atomics once per block.
+constexpr int C5W_TW = 32, C5W_TH = 16;
 template <int OC>
-__global__ void __launch_bounds__(((OC * OC * 25 + 31) / 32) * 32)
+__global__ void __launch_bounds__((OC * OC * C5W_TH + 31) / 32 * 32)
 conv5_wgrad_tiled_kernel(const float* __restrict__ P, const float* __restrict__ dpred, float* __restrict__ g_w, int B, int H,
                          int W) {
-  __shared__ float tp[OC][C5W_TH + 4][C5W_TW + 4];
-  __shared__ float td[OC][C5W_TH][C5W_TW];
-  const int nthr = ((OC * OC * 25 + 31) / 32) * 32;
+  constexpr int TPP = C5W_TW + 5, TDP = C5W_TW + 1;  // padded pitches: bank = 5y / y (conflict free over the 16 rows)
+  __shared__ float tp[OC][C5W_TH + 4][TPP];
+  __shared__ float td[OC][C5W_TH][TDP];
+  constexpr int nthr = (OC * OC * C5W_TH + 31) / 32 * 32;  // whole warps: the shuffle fold below uses the full mask
   const int tix = threadIdx.x;
-  const int dx = tix % 5, dy = (tix / 5) % 5, ic = (tix / 25) % OC, o = tix / (25 * OC);
-  float acc = 0.f;
+  const int y = tix % C5W_TH, pair = tix / C5W_TH;
+  const bool valid = pair < OC * OC;  // padding threads of the last warp compute on pair 0 and write nothing
+  const int ic = valid ? pair % OC : 0, o = valid ? pair / OC : 0;
+  float acc[25];
+#pragma unroll
+  for (int k = 0; k < 25; ++k) acc[k] = 0.f;
   const int tiles_x = W / C5W_TW, tiles_y = H / C5W_TH;
-  // each block sweeps a few tiles so that the final atomics are amortised
   for (int tile_id = blockIdx.x; tile_id < B * tiles_x * tiles_y; tile_id += gridDim.x) {
     const int b = tile_id / (tiles_x * tiles_y);
     const int tr = tile_id % (tiles_x * tiles_y);
@@ -399,14 +425,34 @@ conv5_wgrad_tiled_kernel(const float* __restrict__ P, const float* __restrict__ 
       td[c][yy][xx] = dpred[(((long)b * OC + c) * H + ty0 + yy) * W + tx0 + xx];
     }
     __syncthreads();
-    if (tix < OC * OC * 25) {
-      for (int y = 0; y < C5W_TH; ++y) {
-#pragma unroll 8
-        for (int x = 0; x < C5W_TW; ++x) acc = fmaf(td[o][y][x], tp[ic][y + dy][x + dx], acc);
+    float win[5][5];  // win[dy][j] = tp[ic][y + dy][x + j]
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) win[dy][j + 1] = tp[ic][y + dy][j];
+#pragma unroll 4
+    for (int x = 0; x < C5W_TW; ++x) {
+      const float d = td[o][y][x];
+#pragma unroll
+      for (int dy = 0; dy < 5; ++dy) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) win[dy][j] = win[dy][j + 1];
+        win[dy][4] = tp[ic][y + dy][x + 4];
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) acc[dy * 5 + dx] = fmaf(d, win[dy][dx], acc[dy * 5 + dx]);
       }
     }
   }
-  if (tix < OC * OC * 25) atomicAdd(g_w + tix, acc);
+  // fold the 16 tile rows of each (o, ic) pair (one half-warp) and add the 25 taps to the gradient
+#pragma unroll
+  for (int k = 0; k < 25; ++k) {
+    float v = acc[k];
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if (y == 0 && valid) atomicAdd(g_w + pair * 25 + k, v);
+  }
 }
 
 // ---- loss (scOT/model.py:1425-1484) --------------------------------------------------------------------
@@ -529,8 +575,15 @@ int scot_scale_add_fwd_launch(const float* in, const float* z, const float* gamm
 }
 int scot_scale_add_bwd_launch(const float* g, const void* zb, const float* gamma, void* dz, float* g_gamma, float* g_bias,
                               long rows, int C, cudaStream_t st) {
-  scale_add_bwd_kernel<<<(unsigned)((rows + 63) / 64), 256, 0, st>>>(g, (const bf16*)zb, gamma, (bf16*)dz, g_gamma, g_bias,
-                                                                   rows, C);
+  SCOT_REQUIRE(C % 4 == 0 && C / 4 <= 256, "scale_add_bwd: C must be a multiple of 4 and at most 1024");
+  const int c4n = C / 4, rpp = 256 / c4n;
+  // about two blocks per SM, each sweeping a multiple of the rows-per-pass (at least 8 passes)
+  long rpb = (rows + 295) / 296;
+  if (rpb < 8L * rpp) rpb = 8L * rpp;
+  rpb = (rpb + rpp - 1) / rpp * rpp;
+  const size_t smem = (size_t)rpp * c4n * 2 * sizeof(float4);
+  scale_add_bwd_kernel<<<(unsigned)((rows + rpb - 1) / rpb), 256, smem, st>>>(g, (const bf16*)zb, gamma, (bf16*)dz, g_gamma,
+                                                                              g_bias, rows, C, (int)rpb);
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -590,7 +643,7 @@ int scot_conv5_bwd_launch(const float* P, const float* w, const float* dpred, fl
   switch (OC) {
 #define C5B(N) C5_DISPATCH(N, (conv5_tiled_kernel<N, true><<<grid, 256, 0, st>>>(dpred, w, nullptr, 0, nullptr, nullptr, 0, dP_scratch, B, H, W)); \
                              scot_count_launch(); \
-                             (conv5_wgrad_tiled_kernel<N><<<wg_blocks, ((N * N * 25 + 31) / 32) * 32, 0, st>>>(P, dpred, g_w, B, H, W)))
+                             (conv5_wgrad_tiled_kernel<N><<<wg_blocks, (N * N * 16 + 31) / 32 * 32, 0, st>>>(P, dpred, g_w, B, H, W)))
     C5B(1) C5B(2) C5B(3) C5B(4) C5B(5) C5B(6)
 #undef C5B
   }

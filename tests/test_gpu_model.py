@@ -94,6 +94,11 @@ def test_gradients_match_oracle_smooth_objective(name):
     big = torch.tensor([rel(grads[k], gref[k]) for k in grads
                         if grads[k].dim() >= 2 and "continuous_position_bias_mlp" not in k and grads[k].numel() >= 4096])
     assert float(big.quantile(0.9)) < 0.15 and float(big.max()) < 0.9
+    # small tensors produced by dedicated reduction kernels (5x5 conv weight gradient, ConvNeXt layer scale / bias sums)
+    for k in grads:
+        if k == "patch_recovery.mixup.weight" or (k.startswith("residual_blocks.") and (k.endswith(".weight") and k.count(".") == 3
+                                                                                         or k.endswith("pwconv2.bias"))):
+            assert rel(grads[k], gref[k]) < 0.12, (k, rel(grads[k], gref[k]))
 
 
 def test_loss_gradient_mse_objective():
