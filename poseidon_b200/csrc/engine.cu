@@ -7,6 +7,7 @@
 // forward+backward is a fixed sequence of kernel launches on the caller's stream and can be captured in
 // a CUDA graph.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -89,6 +90,7 @@ struct ScotEngine {
   size_t z32, y32;                       // fp32 scratch [M0*C0] each
   // backward scratch
   size_t dzb, dzb2, dqkv, dh, dob, partial, dpre, dpred, dD16, dgrads_zero_begin, dgrads_zero_bytes;
+  size_t dzbB, dzb2B, dqkvB, dhB, dobB;  // second set of block-backward scratch (blocks alternate, see block_bwd)
   size_t partial_bytes;
   std::vector<size_t> gstage;            // fp32 [M_s, C_s]
   std::vector<ScotCpbTable> cpb_tables;  // relative-position-bias MLPs of all attention layers (<= 64 per table)
@@ -100,6 +102,11 @@ struct ScotEngine {
   int last_mask_mode = 0;
   float* last_pred = nullptr;
   bool have_forward = false;
+  // side stream for the weight-gradient GEMMs of the block backward (fork/join with events; capturable)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+  bool join_pending[2] = {false, false};
+  int overlap = -1;  // SCOT_WGRAD_OVERLAP (default on)
 };
 
 namespace {
@@ -338,6 +345,11 @@ int build_plan(ScotEngine* e) {
   e->dqkv = b.take(M0 * 3 * C0 * 2);
   e->dh = b.take(max_h * 2);
   e->dob = b.take(M0 * C0 * 2);
+  e->dzbB = b.take(M0 * C0 * 2);
+  e->dzb2B = b.take(M0 * C0 * 2);
+  e->dqkvB = b.take(M0 * 3 * C0 * 2);
+  e->dhB = b.take(max_h * 2);
+  e->dobB = b.take(M0 * C0 * 2);
   size_t pb = 0;
   for (int s = 0; s < e->ns; ++s) {
     const Geo& g = e->geo[s];
@@ -458,16 +470,35 @@ int block_fwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, in
   return 0;
 }
 
+// main stream waits until the side-stream work that used scratch set `set` has finished
+int join_side(const Ctx& c, int set) {
+  ScotEngine* e = c.e;
+  if (e->join_pending[set]) {
+    SCOT_CHECK_CUDA(cudaStreamWaitEvent(c.st, e->ev_join[set], 0));
+    e->join_pending[set] = false;
+  }
+  return 0;
+}
+int join_all(const Ctx& c) {
+  RC(join_side(c, 0));
+  RC(join_side(c, 1));
+  return 0;
+}
+
 // g: gradient wrt the block output on entry, wrt the block input on exit (fp32, in place).
 // The four weight-gradient GEMMs are side branches of the chain: their operands stay alive until the end of the block
-// (separate dz buffers for the two norms), so they are issued as ONE grouped launch after the data-gradient chain.
-int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, int shift, float* gr, const bf16* xb_in) {
-  const ScotEngine* e = c.e;
+// (separate dz buffers for the two norms), so they are issued as ONE grouped launch after the data-gradient chain — on
+// a second stream: consecutive blocks alternate between two sets of scratch buffers (`set`), so the weight gradients
+// of block i run concurrently with the data-gradient chain of block i-1 (fork / join through events; the pattern is
+// captured into the CUDA graph as parallel branches). At the deep stages both are small, latency-bound kernels.
+int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, int shift, float* gr, const bf16* xb_in, int set) {
+  ScotEngine* e = c.e;
   const long M = g.M, C = g.C, H = hidden_of(e, g.C);
   const int T = g.res * g.res;
-  bf16* dzb = c.at<bf16>(e->dzb);
-  bf16* dzb2 = c.at<bf16>(e->dzb2);
-  bf16* dh = c.at<bf16>(e->dh);
+  RC(join_side(c, set));  // the weight gradients issued two blocks ago read this scratch set
+  bf16* dzb = c.at<bf16>(set ? e->dzbB : e->dzb);
+  bf16* dzb2 = c.at<bf16>(set ? e->dzb2B : e->dzb2);
+  bf16* dh = c.at<bf16>(set ? e->dhB : e->dh);
   // y = y1 + LN2(mlp(y1))
   RC(norm_bwd(c, p.ln2, gr, c.at<bf16>(b.zhat2), c.at<float>(b.rstd2), dzb2, 0, c.g(p.b2), M, (int)C, T, 0));
   RC(gemm(c, dzb2, C, 0, c.w16(p.w2), H, 1, M, H, C, SCOT_EPI_GELU_BWD, nullptr, dh, H, nullptr, 0, c.at<bf16>(b.h), H,
@@ -475,21 +506,30 @@ int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, in
   RC(gemm(c, dh, H, 0, c.w16(p.w1), C, 1, M, C, H, SCOT_EPI_RMW_F32, nullptr, gr, C));
   // y1 = x + LN1(attn(x))
   RC(norm_bwd(c, p.ln1, gr, c.at<bf16>(b.zhat1), c.at<float>(b.rstd1), dzb, 0, c.g(p.bo), M, (int)C, T, 0));
-  bf16* dob = c.at<bf16>(e->dob);
+  bf16* dob = c.at<bf16>(set ? e->dobB : e->dob);
   RC(gemm(c, dzb, C, 0, c.w16(p.wo), C, 1, M, C, C, SCOT_EPI_BF16, nullptr, dob, C));
-  bf16* dqkv = c.at<bf16>(e->dqkv);
+  bf16* dqkv = c.at<bf16>(set ? e->dqkvB : e->dqkv);
   RC(scot_attn_bwd_launch(c.at<bf16>(b.qkv), c.at<bf16>(b.o), dob, c.at<float>(b.lse), c.at<float>(b.tab2),
                           c.at<float>(b.alpha), dqkv, c.at<float>(e->partial), e->partial_bytes, c.at<float>(b.dtab),
                           c.at<float>(b.dalpha), c.g(p.bqkv), c.g(p.bqkv + 2 * C), e->batch, g.res, g.ws, shift, g.heads,
                           g.hd, c.st));
-  RC(gemm(c, dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
   const ScotWgradProblem wg[4] = {
       {dzb2, C, c.at<bf16>(b.g), H, c.g(p.w2), H, M, (int)C, (int)H},         // output.dense
       {dh, H, c.at<bf16>(b.y1b), C, c.g(p.w1), C, M, (int)H, (int)C},         // intermediate.dense
       {dzb, C, c.at<bf16>(b.o), C, c.g(p.wo), C, M, (int)C, (int)C},          // attention.output.dense
       {dqkv, 3 * C, xb_in, C, c.g(p.wqkv), C, M, (int)(3 * C), (int)C},       // query | key | value
   };
-  RC(scot_gemm_wgrad_group_launch(wg, 4, c.impl, c.st));
+  if (e->overlap && e->side != nullptr) {
+    SCOT_CHECK_CUDA(cudaEventRecord(e->ev_fork[set], c.st));  // all four dY operands are complete here
+    SCOT_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork[set], 0));
+    RC(scot_gemm_wgrad_group_launch(wg, 4, c.impl, e->side));
+    SCOT_CHECK_CUDA(cudaEventRecord(e->ev_join[set], e->side));
+    e->join_pending[set] = true;
+    RC(gemm(c, dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
+  } else {
+    RC(gemm(c, dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
+    RC(scot_gemm_wgrad_group_launch(wg, 4, c.impl, c.st));
+  }
   return 0;
 }
 
@@ -544,7 +584,17 @@ int scot_engine_create(const ScotModelDesc* desc, int batch, ScotEngine** out) {
   return 0;
 }
 
-void scot_engine_destroy(ScotEngine* e) { delete e; }
+void scot_engine_destroy(ScotEngine* e) {
+  if (e == nullptr) return;
+  if (e->side != nullptr) {
+    cudaStreamDestroy(e->side);
+    for (int k = 0; k < 2; ++k) {
+      if (e->ev_fork[k]) cudaEventDestroy(e->ev_fork[k]);
+      if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]);
+    }
+  }
+  delete e;
+}
 
 long scot_engine_num_params(const ScotEngine* e) { return (long)e->params.size(); }
 long scot_engine_param_elems(const ScotEngine* e) { return e->n_elems; }
@@ -711,6 +761,18 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
   const Geo& g0 = e->geo[0];
   const int NR = d.num_out_channels * d.patch_size * d.patch_size;
   const long HW = (long)d.image_size * d.image_size;
+  if (e->overlap < 0) {
+    const char* ev = getenv("SCOT_WGRAD_OVERLAP");
+    e->overlap = (ev != nullptr && ev[0] == '0') ? 0 : 1;
+  }
+  if (e->overlap && e->side == nullptr) {
+    SCOT_CHECK_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      SCOT_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_fork[k], cudaEventDisableTiming));
+      SCOT_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
+    }
+  }
+  e->join_pending[0] = e->join_pending[1] = false;
   SCOT_CHECK_CUDA(cudaMemsetAsync(c.at<uint8_t>(e->dgrads_zero_begin), 0, e->dgrads_zero_bytes, c.st));
   // ---- loss + patch recovery backward ----
   float* dpred = c.at<float>(e->dpred);
@@ -738,8 +800,9 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
       if (bi > 0) xb_in = c.at<bf16>(e->dbuf[j][bi - 1].xbout);
       else if (j == 0) xb_in = (d.skip_blocks[s] > 0) ? c.at<bf16>(e->skip_xb[s]) : c.at<bf16>(e->ebuf[s].back().xbout);
       else xb_in = c.at<bf16>(e->u_xb[j - 1]);
-      RC(block_bwd(c, e->dec[j][bi], e->dbuf[j][bi], g, shift_of(g, orig), gr, xb_in));
+      RC(block_bwd(c, e->dec[j][bi], e->dbuf[j][bi], g, shift_of(g, orig), gr, xb_in, bi & 1));
     }
+    RC(join_all(c));  // the code below reuses the scratch buffers on the main stream
     if (j > 0) {
       // gr = grad wrt (mixup(norm(shuffle(upsample(x_coarse)))) + skip[s]); the skip part stays in gstage[s]
       const int jc = j - 1;  // decoder layer that produced this stage's input
@@ -804,8 +867,9 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
       if (i > 0) xb_in = c.at<bf16>(e->ebuf[s][i - 1].xbout);
       else if (s == 0) xb_in = c.at<bf16>(e->emb_xb);
       else xb_in = c.at<bf16>(e->m_xb[s - 1]);
-      RC(block_bwd(c, e->enc[s][i], e->ebuf[s][i], g, shift_of(g, i), gr, xb_in));
+      RC(block_bwd(c, e->enc[s][i], e->ebuf[s][i], g, shift_of(g, i), gr, xb_in, i & 1));
     }
+    RC(join_all(c));
     if (s < ns - 1) {
       // the stage input also feeds the merge through `hidden + inputs` (model.py:847-849)
       RC(scot_merge_scatter_launch(c.at<float>(e->z32), gr, gr, B, g.res, g.C, c.st));
