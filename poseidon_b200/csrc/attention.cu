@@ -993,8 +993,20 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
   chunks = ceil_div(total_windows, wpc);
   (void)partial;
   (void)partial_bytes;
-  // dk/dv kernel: ~66 KB of smem -> three CTAs per SM
-  int chunks2 = (3 * num_sms()) / (g.heads * C2::KG);
+  // dk/dv kernel: size the grid to ONE wave of what is actually resident (two CTAs per SM at 128 registers x 256
+  // threads; the occupancy API accounts for registers and shared memory) — a 1.3-wave grid costs a second, mostly
+  // empty pass over the SMs
+  static int occ2 = 0;
+  if (occ2 == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, attn_bwd_dkv_kernel<WS, HD, NWARP, false>, NWARP * 32, C2::smem) != cudaSuccess || nb < 1)
+      nb = 1;
+    int nb_s = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_s, attn_bwd_dkv_kernel<WS, HD, NWARP, true>, NWARP * 32, C2::smem) != cudaSuccess || nb_s < 1)
+      nb_s = 1;
+    occ2 = nb < nb_s ? nb : nb_s;
+  }
+  int chunks2 = (occ2 * num_sms()) / (g.heads * C2::KG);
   if (chunks2 > iters) chunks2 = iters;
   if (chunks2 < 1) chunks2 = 1;
   const int wpc2 = ceil_div(iters, chunks2) * C2::WPI;
