@@ -172,6 +172,9 @@ int scot_grad_sq_norm(const float* grads, long n_elems, float* out, void* stream
 int scot_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16,
                     const uint8_t* chunk_group, long n_elems, const float* group_hp, int n_groups, const float* grad_sq_norm,
                     float max_norm, float grad_scale, void* stream);
+/* Evaluation metric reductions (scOT/metrics.py:12-36): out[(b*C + c)*2 + {0,1}] = sum_pixels |pred - labels|^p, |labels|^p
+ * for every (sample, channel) plane of `hw` pixels; `planes` = B*C. */
+int scot_lp_plane_sums(const float* pred, const float* labels, float* out, int p, long planes, long hw, void* stream);
 /* Re-binds the tensors the next scot_engine_backward reads (the inputs / prediction of a forward that was replayed
  * from a CUDA graph, where the host-side bookkeeping of scot_engine_forward did not run). Host-only, no launch. */
 int scot_engine_bind_io(ScotEngine* e, const float* pixel_values, const float* time, const float* labels,

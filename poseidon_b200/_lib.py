@@ -154,6 +154,8 @@ def _declare_engine(lib):
     lib.scot_grad_sq_norm.restype = i
     lib.scot_adamw_step.argtypes = [vp] * 6 + [l, vp, i, vp, f, f, vp]
     lib.scot_adamw_step.restype = i
+    lib.scot_lp_plane_sums.argtypes = [vp, vp, vp, i, l, l, vp]
+    lib.scot_lp_plane_sums.restype = i
 
 
 _declare_base = _declare

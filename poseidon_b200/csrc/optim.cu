@@ -112,3 +112,56 @@ int scot_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Evaluation metrics on the device: per-(sample, channel) sums of |pred - y|^p and |y|^p —
+// the two reductions behind scOT/metrics.py:12-36 `relative_lp_error` — so that an evaluation pass moves
+// 2 * B * C floats to the host instead of the full [N, C, 128, 128] predictions (scOT/train.py:344-398).
+// One block per (sample, channel) plane, fixed summation order: deterministic.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+lp_plane_sums_kernel(const float* __restrict__ pred, const float* __restrict__ labels, float* __restrict__ out, int p, long HW) {
+  const long plane = blockIdx.x;
+  const float* a = pred + plane * HW;
+  const float* b = labels + plane * HW;
+  float num = 0.f, den = 0.f;
+  for (long k = threadIdx.x; k < HW; k += blockDim.x) {
+    const float y = b[k], d = fabsf(a[k] - y), ay = fabsf(y);
+    if (p == 1) {
+      num += d;
+      den += ay;
+    } else if (p == 2) {
+      num += d * d;
+      den += ay * ay;
+    } else {
+      num += powf(d, (float)p);
+      den += powf(ay, (float)p);
+    }
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  __shared__ float s1[8], s2[8];
+  if ((threadIdx.x & 31) == 0) {
+    s1[threadIdx.x >> 5] = num;
+    s2[threadIdx.x >> 5] = den;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = 0.f, y = 0.f;
+    for (int k = 0; k < 8; ++k) {
+      x += s1[k];
+      y += s2[k];
+    }
+    out[plane * 2 + 0] = x;
+    out[plane * 2 + 1] = y;
+  }
+}
+}  // namespace
+
+extern "C" int scot_lp_plane_sums(const float* pred, const float* labels, float* out, int p, long planes, long hw, void* stream) {
+  SCOT_REQUIRE(pred && labels && out && planes > 0 && hw > 0 && p >= 1, "lp_plane_sums: bad arguments");
+  lp_plane_sums_kernel<<<(unsigned)planes, 256, 0, (cudaStream_t)stream>>>(pred, labels, out, p, hw);
+  SCOT_LAUNCH_CHECK();
+  return 0;
+}
