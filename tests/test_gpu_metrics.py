@@ -37,6 +37,8 @@ def test_error_statistics_match_compute_metrics():
     got = M.error_statistics(pred.cuda(), y.cuda(), sl, ["rho", "uv", "p", "tr"])
     for name, r in zip(["rho", "uv", "p", "tr"], ref):
         for k, v in r.items():
-            assert abs(got[name + "/" + k] - v) < 1e-5 * abs(v) + 1e-7, (name, k)
+            # errors are ~100 (percent); fp32 plane sums carry ~1e-7 relative error, which the std (a difference of
+            # nearly equal numbers) sees in absolute terms
+            assert abs(got[name + "/" + k] - v) < 1e-5 * abs(v) + 1e-4, (name, k)
     assert abs(got["mean_relative_l1_error"] - np.mean([r["mean_relative_l1_error"] for r in ref])) < 1e-4
     assert abs(got["mean_over_median_relative_l1_error"] - np.mean([r["median_relative_l1_error"] for r in ref])) < 1e-4
