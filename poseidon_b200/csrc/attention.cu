@@ -970,7 +970,7 @@ int launch_fwd(const void* qkv, void* out, float* lse, const float* tab2, const 
 template <int WS, int HD, int NWARP>
 int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, const float* tab2, const float* alpha,
                void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha, float* g_qbias,
-               float* g_vbias, WinGeom g, int total_windows, cudaStream_t st) {
+               float* g_vbias, WinGeom g, int total_windows, cudaStream_t st, const ScotAttnBwdFork* fk) {
   using C1 = DqCfg<WS, HD, NWARP>;
   using C2 = DkvCfg<WS, HD, NWARP>;
   static bool done = false;
@@ -1012,13 +1012,27 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
   const int wpc2 = ceil_div(iters, chunks2) * C2::WPI;
   chunks2 = ceil_div(total_windows, wpc2);
   dim3 grid1(g.heads, C1::RG, chunks);
+  dim3 grid2(g.heads, C2::KG, chunks2);
+  // The two kernels are independent (disjoint column ranges of dqkv, each recomputes P from the saved LSE). With a fork
+  // descriptor the dk/dv kernel goes to a second stream and runs beside the dq kernel: at the small-window stages both are
+  // latency-bound grids that leave most of the machine idle.
+  if (fk != nullptr) {
+    SCOT_CHECK_CUDA(cudaEventRecord(fk->fork, st));
+    SCOT_CHECK_CUDA(cudaStreamWaitEvent(fk->stream, fk->fork, 0));
+    SCOT_CHECK_CUDA(scot_launch_pdl(k2, grid2, dim3(NWARP * 32), C2::smem, fk->stream, (const bf16*)qkv, (const bf16*)o,
+                                    (const bf16*)d_o, lse, tab2, alpha, (bf16*)dqkv, g_vbias, g, total_windows, wpc2));
+    SCOT_LAUNCH_CHECK();
+    SCOT_CHECK_CUDA(cudaEventRecord(fk->join, fk->stream));
+  }
   SCOT_CHECK_CUDA(scot_launch_pdl(k1, grid1, dim3(NWARP * 32), C1::smem, st, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
                                   tab2, alpha, (bf16*)dqkv, dtab, dalpha, g_qbias, g, total_windows, wpc));
   SCOT_LAUNCH_CHECK();
-  dim3 grid2(g.heads, C2::KG, chunks2);
-  SCOT_CHECK_CUDA(scot_launch_pdl(k2, grid2, dim3(NWARP * 32), C2::smem, st, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
-                                  tab2, alpha, (bf16*)dqkv, g_vbias, g, total_windows, wpc2));
-  SCOT_LAUNCH_CHECK();
+  if (fk == nullptr) {
+    SCOT_CHECK_CUDA(scot_launch_pdl(k2, grid2, dim3(NWARP * 32), C2::smem, st, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse,
+                                    tab2, alpha, (bf16*)dqkv, g_vbias, g, total_windows, wpc2));
+    SCOT_LAUNCH_CHECK();
+  }
+  if (fk != nullptr) SCOT_CHECK_CUDA(cudaStreamWaitEvent(st, fk->join, 0));
   return 0;
 }
 
@@ -1084,10 +1098,19 @@ int scot_attn_bwd_launch(const void* qkv, const void* o, const void* d_o, const 
                          const float* alpha, void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha,
                          float* g_qbias, float* g_vbias, int batch, int res, int ws, int shift, int heads, int hd,
                          cudaStream_t st) {
+  return scot_attn_bwd_launch2(qkv, o, d_o, lse, tab2, alpha, dqkv, partial, partial_bytes, dtab, dalpha, g_qbias, g_vbias,
+                               batch, res, ws, shift, heads, hd, st, nullptr);
+}
+
+int scot_attn_bwd_launch2(const void* qkv, const void* o, const void* d_o, const float* lse, const float* tab2,
+                          const float* alpha, void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha,
+                          float* g_qbias, float* g_vbias, int batch, int res, int ws, int shift, int heads, int hd,
+                          cudaStream_t st, const ScotAttnBwdFork* fk) {
   SCOT_REQUIRE(qkv && o && d_o && lse && tab2 && alpha && dqkv && dtab && dalpha, "attn_bwd: null pointer");
+  SCOT_REQUIRE(fk == nullptr || (fk->stream != nullptr && fk->fork != nullptr && fk->join != nullptr), "attn_bwd: bad fork descriptor");
   WinGeom g{res, shift, res / ws, heads, heads * hd};
   const int tw = batch * g.nws * g.nws;
-#define BWD_ARGS qkv, o, d_o, lse, tab2, alpha, dqkv, partial, partial_bytes, dtab, dalpha, g_qbias, g_vbias, g, tw, st
+#define BWD_ARGS qkv, o, d_o, lse, tab2, alpha, dqkv, partial, partial_bytes, dtab, dalpha, g_qbias, g_vbias, g, tw, st, fk
   ATTN_DISPATCH(16, 16, (launch_bwd<16, 16, 8>(BWD_ARGS)))
   ATTN_DISPATCH(16, 32, (launch_bwd<16, 32, 8>(BWD_ARGS)))
   ATTN_DISPATCH(16, 64, (launch_bwd<16, 64, 4>(BWD_ARGS)))

@@ -107,6 +107,17 @@ struct ScotEngine {
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   bool join_pending[2] = {false, false};
   int overlap = -1;  // SCOT_WGRAD_OVERLAP (default on)
+  // second side stream: the ConvNeXt blocks on the skip connections are side branches of the U-Net (needed only when the
+  // decoder / the encoder backward reaches their stage), so they run concurrently with the latency-bound deep stages
+  cudaStream_t side2 = nullptr;
+  cudaEvent_t ev_cfork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_cjoin[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool cjoin_pending[4] = {false, false, false, false};
+  int cnx_overlap = -1;  // SCOT_CNX_OVERLAP
+  size_t z32C = 0, y32C = 0, dzbC = 0, dhC = 0;  // private scratch of the ConvNeXt side branch
+  // third stream: dk/dv kernel of the window-attention backward beside the dq kernel (small-window stages)
+  cudaStream_t side3 = nullptr;
+  cudaEvent_t ev_afork = nullptr, ev_ajoin = nullptr;
+  int attn_split_ws = -1;  // SCOT_ATTN_BWD_SPLIT = largest window size that forks (0 = never)
 };
 
 namespace {
@@ -402,6 +413,18 @@ int build_plan(ScotEngine* e) {
   }
   e->gstage.resize(e->ns);
   for (int s = 0; s < e->ns; ++s) e->gstage[s] = b.take((size_t)e->geo[s].M * e->geo[s].C * 4);
+  {
+    // scratch of the ConvNeXt side branch (largest stage that has skip blocks and is not the deepest one)
+    size_t mc = 0;
+    for (int s = 0; s + 1 < e->ns; ++s)
+      if (d.skip_blocks[s] > 0) mc = std::max(mc, (size_t)e->geo[s].M * e->geo[s].C);
+    if (mc > 0) {
+      e->z32C = b.take(mc * 4);
+      e->y32C = b.take(mc * 4);
+      e->dzbC = b.take(mc * 2);
+      e->dhC = b.take(mc * 4 * 2);
+    }
+  }
   e->ws_bytes = b.off;
   return 0;
 }
@@ -509,10 +532,12 @@ int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, in
   bf16* dob = c.at<bf16>(set ? e->dobB : e->dob);
   RC(gemm(c, dzb, C, 0, c.w16(p.wo), C, 1, M, C, C, SCOT_EPI_BF16, nullptr, dob, C));
   bf16* dqkv = c.at<bf16>(set ? e->dqkvB : e->dqkv);
-  RC(scot_attn_bwd_launch(c.at<bf16>(b.qkv), c.at<bf16>(b.o), dob, c.at<float>(b.lse), c.at<float>(b.tab2),
-                          c.at<float>(b.alpha), dqkv, c.at<float>(e->partial), e->partial_bytes, c.at<float>(b.dtab),
-                          c.at<float>(b.dalpha), c.g(p.bqkv), c.g(p.bqkv + 2 * C), e->batch, g.res, g.ws, shift, g.heads,
-                          g.hd, c.st));
+  ScotAttnBwdFork fk{e->side3, e->ev_afork, e->ev_ajoin};
+  const bool fork_attn = e->side3 != nullptr && g.ws <= e->attn_split_ws;
+  RC(scot_attn_bwd_launch2(c.at<bf16>(b.qkv), c.at<bf16>(b.o), dob, c.at<float>(b.lse), c.at<float>(b.tab2),
+                           c.at<float>(b.alpha), dqkv, c.at<float>(e->partial), e->partial_bytes, c.at<float>(b.dtab),
+                           c.at<float>(b.dalpha), c.g(p.bqkv), c.g(p.bqkv + 2 * C), e->batch, g.res, g.ws, shift, g.heads,
+                           g.hd, c.st, fork_attn ? &fk : nullptr));
   const ScotWgradProblem wg[4] = {
       {dzb2, C, c.at<bf16>(b.g), H, c.g(p.w2), H, M, (int)C, (int)H},         // output.dense
       {dh, H, c.at<bf16>(b.y1b), C, c.g(p.w1), C, M, (int)H, (int)C},         // intermediate.dense
@@ -530,6 +555,116 @@ int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, in
     RC(gemm(c, dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
     RC(scot_gemm_wgrad_group_launch(wg, 4, c.impl, c.st));
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ConvNeXt blocks on the skip connection of stage s (scOT/model.py:198-217, 1388-1393) and their backward.
+// `z32` / `y32` / `dzb` / `dh` are scratch buffers: the main-stream instances when the blocks run in line, the private
+// *C set when they run as a side branch on e->side2.
+// ---------------------------------------------------------------------------------------------------
+struct CnxScratch {
+  float* z32;
+  float* y32;
+  bf16* dzb;
+  bf16* dh;
+};
+CnxScratch cnx_scratch(const Ctx& c, bool side) {
+  const ScotEngine* e = c.e;
+  if (side) return CnxScratch{c.at<float>(e->z32C), c.at<float>(e->y32C), c.at<bf16>(e->dzbC), c.at<bf16>(e->dhC)};
+  return CnxScratch{c.at<float>(e->z32), c.at<float>(e->y32), c.at<bf16>(e->dzb), c.at<bf16>(e->dh)};
+}
+
+// returns (through skip_io) the fp32 output of the last block
+int cnx_fwd_stage(const Ctx& c, int s, const float** skip_io, const CnxScratch& sc) {
+  const ScotEngine* e = c.e;
+  const ScotModelDesc& d = e->d;
+  const Geo& g = e->geo[s];
+  const int B = e->batch;
+  const float* skip = *skip_io;
+  for (int k = 0; k < d.skip_blocks[s]; ++k) {
+    const CnxP& p = e->cnx[s][k];
+    const CnxBuf& b = e->cbuf[s][k];
+    RC(scot_dwconv7_fwd_launch(skip, c.p(p.wdw), c.p(p.bdw), sc.z32, B, g.res, g.C, c.st));
+    RC(norm_fwd(c, p.norm, sc.z32, nullptr, nullptr, c.at<bf16>(b.nb), c.at<bf16>(b.zhat), c.at<float>(b.rstd), g.M, g.C,
+                g.res * g.res, 0, d.layer_norm_eps));
+    RC(gemm(c, c.at<bf16>(b.nb), g.C, 0, c.w16(p.w1), g.C, 0, g.M, 4L * g.C, g.C, SCOT_EPI_GELU, c.p(p.b1), c.at<bf16>(b.h),
+            4L * g.C, c.at<bf16>(b.g), 4L * g.C));
+    RC(gemm(c, c.at<bf16>(b.g), 4L * g.C, 0, c.w16(p.w2), 4L * g.C, 0, g.M, g.C, 4L * g.C, SCOT_EPI_F32, c.p(p.b2), sc.z32,
+            g.C));
+    RC(scot_scale_add_fwd_launch(skip, sc.z32, c.p(p.gamma), c.at<float>(b.out), c.at<bf16>(b.z2b), g.M, g.C, c.st));
+    skip = c.at<float>(b.out);
+  }
+  *skip_io = skip;
+  return 0;
+}
+
+// gr: gradient wrt the post-ConvNeXt skip on entry, wrt the encoder stage output on exit (fp32, in place)
+int cnx_bwd_stage(const Ctx& c, int s, float* gr, const CnxScratch& sc) {
+  const ScotEngine* e = c.e;
+  const ScotModelDesc& d = e->d;
+  const Geo& g = e->geo[s];
+  const int B = e->batch;
+  for (int k = d.skip_blocks[s] - 1; k >= 0; --k) {
+    const CnxP& p = e->cnx[s][k];
+    const CnxBuf& b = e->cbuf[s][k];
+    const float* blk_in = (k == 0) ? c.at<float>(e->ebuf[s].back().xout) : c.at<float>(e->cbuf[s][k - 1].out);
+    RC(scot_scale_add_bwd_launch(gr, c.at<bf16>(b.z2b), c.p(p.gamma), sc.dzb, c.g(p.gamma), c.g(p.b2), g.M, g.C, c.st));
+    RC(gemm(c, sc.dzb, g.C, 0, c.w16(p.w2), 4L * g.C, 1, g.M, 4L * g.C, g.C, SCOT_EPI_GELU_BWD, nullptr, sc.dh, 4L * g.C,
+            nullptr, 0, c.at<bf16>(b.h), 4L * g.C, c.g(p.b1)));
+    RC(gemm(c, sc.dh, 4L * g.C, 0, c.w16(p.w1), g.C, 1, g.M, g.C, 4L * g.C, SCOT_EPI_F32, nullptr, sc.z32, g.C));
+    const ScotWgradProblem wg[2] = {
+        {sc.dzb, g.C, c.at<bf16>(b.g), 4L * g.C, c.g(p.w2), 4L * g.C, g.M, g.C, 4 * g.C},  // pwconv2
+        {sc.dh, 4L * g.C, c.at<bf16>(b.nb), g.C, c.g(p.w1), g.C, g.M, 4 * g.C, g.C},        // pwconv1
+    };
+    RC(scot_gemm_wgrad_group_launch(wg, 2, c.impl, c.st));
+    RC(norm_bwd(c, p.norm, sc.z32, c.at<bf16>(b.zhat), c.at<float>(b.rstd), sc.y32, 1, c.g(p.bdw), g.M, g.C, g.res * g.res,
+                0));
+    RC(scot_dwconv7_bwd_launch(blk_in, c.p(p.wdw), sc.y32, gr, gr, c.g(p.wdw), B, g.res, g.C, c.st));
+  }
+  return 0;
+}
+
+// Side-branch plumbing: fork e->side2 from the main stream, run `fn` there, record the join event of stage s.
+int cnx_side_init(ScotEngine* e) {
+  if (e->cnx_overlap < 0) {
+    const char* ev = getenv("SCOT_CNX_OVERLAP");
+    e->cnx_overlap = (ev != nullptr && ev[0] == '1') ? 1 : 0;
+  }
+  if (e->cnx_overlap && e->z32C == 0 && e->dhC == 0) e->cnx_overlap = 0;  // nothing to overlap
+  if (e->cnx_overlap && e->side2 == nullptr) {
+    SCOT_CHECK_CUDA(cudaStreamCreateWithFlags(&e->side2, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; ++k) {
+      SCOT_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_cfork[k], cudaEventDisableTiming));
+      SCOT_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_cjoin[k], cudaEventDisableTiming));
+    }
+  }
+  for (int k = 0; k < 4; ++k) e->cjoin_pending[k] = false;
+  return 0;
+}
+bool cnx_on_side(const ScotEngine* e, int s) { return e->cnx_overlap && s + 1 < e->ns && e->d.skip_blocks[s] > 0; }
+int cnx_fork(const Ctx& c, int s) {
+  ScotEngine* e = c.e;
+  SCOT_CHECK_CUDA(cudaEventRecord(e->ev_cfork[s], c.st));
+  SCOT_CHECK_CUDA(cudaStreamWaitEvent(e->side2, e->ev_cfork[s], 0));
+  return 0;
+}
+int cnx_mark_join(const Ctx& c, int s) {
+  ScotEngine* e = c.e;
+  SCOT_CHECK_CUDA(cudaEventRecord(e->ev_cjoin[s], e->side2));
+  e->cjoin_pending[s] = true;
+  return 0;
+}
+int cnx_join(const Ctx& c, int s) {
+  ScotEngine* e = c.e;
+  if (e->cjoin_pending[s]) {
+    SCOT_CHECK_CUDA(cudaStreamWaitEvent(c.st, e->ev_cjoin[s], 0));
+    e->cjoin_pending[s] = false;
+  }
+  return 0;
+}
+int cnx_join_all(const Ctx& c) {
+  for (int s = 0; s < c.e->ns; ++s) RC(cnx_join(c, s));
   return 0;
 }
 
@@ -593,6 +728,18 @@ void scot_engine_destroy(ScotEngine* e) {
       if (e->ev_join[k]) cudaEventDestroy(e->ev_join[k]);
     }
   }
+  if (e->side3 != nullptr) {
+    cudaStreamDestroy(e->side3);
+    if (e->ev_afork) cudaEventDestroy(e->ev_afork);
+    if (e->ev_ajoin) cudaEventDestroy(e->ev_ajoin);
+  }
+  if (e->side2 != nullptr) {
+    cudaStreamDestroy(e->side2);
+    for (int k = 0; k < 4; ++k) {
+      if (e->ev_cfork[k]) cudaEventDestroy(e->ev_cfork[k]);
+      if (e->ev_cjoin[k]) cudaEventDestroy(e->ev_cjoin[k]);
+    }
+  }
   delete e;
 }
 
@@ -627,6 +774,7 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
   Ctx c{e, params, nullptr, (uint8_t*)arena, time, (cudaStream_t)stream, gemm_impl};
   const int B = e->batch, ns = e->ns;
   const Geo& g0 = e->geo[0];
+  RC(cnx_side_init(e));
   // bf16 copy of all parameters (GEMM operands)
   RC(scot_cast_f32_bf16_launch(params, c.at<bf16>(e->wb16), e->n_elems, c.st));
   // relative-position-bias tables of every attention layer (batch independent), one launch
@@ -654,6 +802,14 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
     }
     skip[s] = x;
     skipb[s] = xb;
+    if (cnx_on_side(e, s)) {
+      // side branch: needed again only when the decoder comes back up to this stage
+      Ctx cs = c;
+      cs.st = e->side2;
+      RC(cnx_fork(c, s));
+      RC(cnx_fwd_stage(cs, s, &skip[s], cnx_scratch(c, true)));
+      RC(cnx_mark_join(c, s));
+    }
     if (s < ns - 1) {
       const Geo& gn = e->geo[s + 1];
       RC(scot_merge_gather_launch(x, stage_in, c.at<bf16>(e->m_g16[s]), B, g.res, g.C, c.st));
@@ -668,20 +824,7 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
   // ---- ConvNeXt blocks on the skips (model.py:198-217, 1388-1393) ----
   for (int s = 0; s < ns; ++s) {
     const Geo& g = e->geo[s];
-    for (int k = 0; k < d.skip_blocks[s]; ++k) {
-      const CnxP& p = e->cnx[s][k];
-      const CnxBuf& b = e->cbuf[s][k];
-      RC(scot_dwconv7_fwd_launch(skip[s], c.p(p.wdw), c.p(p.bdw), c.at<float>(e->z32), B, g.res, g.C, c.st));
-      RC(norm_fwd(c, p.norm, c.at<float>(e->z32), nullptr, nullptr, c.at<bf16>(b.nb), c.at<bf16>(b.zhat),
-                  c.at<float>(b.rstd), g.M, g.C, g.res * g.res, 0, d.layer_norm_eps));
-      RC(gemm(c, c.at<bf16>(b.nb), g.C, 0, c.w16(p.w1), g.C, 0, g.M, 4L * g.C, g.C, SCOT_EPI_GELU, c.p(p.b1),
-              c.at<bf16>(b.h), 4L * g.C, c.at<bf16>(b.g), 4L * g.C));
-      RC(gemm(c, c.at<bf16>(b.g), 4L * g.C, 0, c.w16(p.w2), 4L * g.C, 0, g.M, g.C, 4L * g.C, SCOT_EPI_F32, c.p(p.b2),
-              c.at<float>(e->z32), g.C));
-      RC(scot_scale_add_fwd_launch(skip[s], c.at<float>(e->z32), c.p(p.gamma), c.at<float>(b.out), c.at<bf16>(b.z2b), g.M,
-                                   g.C, c.st));
-      skip[s] = c.at<float>(b.out);
-    }
+    if (d.skip_blocks[s] > 0 && !cnx_on_side(e, s)) RC(cnx_fwd_stage(c, s, &skip[s], cnx_scratch(c, false)));
     if (d.skip_blocks[s] > 0 && s == ns - 1) {
       RC(scot_cast_f32_bf16_launch(skip[s], c.at<bf16>(e->skip_xb[s]), g.M * g.C, c.st));
       skipb[s] = c.at<bf16>(e->skip_xb[s]);
@@ -706,12 +849,14 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
               2L * g.C));
       RC(norm_fwd(c, p.norm, c.at<float>(e->z32), nullptr, nullptr, c.at<bf16>(e->u_nb[j]), c.at<bf16>(e->u_norm[j].zhat),
                   c.at<float>(e->u_norm[j].rstd), gf.M, gf.C, gf.res * gf.res, g.res, 1e-5f));
+      RC(cnx_join(c, s - 1));  // the post-ConvNeXt skip of the finer stage is the residual of this GEMM
       RC(gemm(c, c.at<bf16>(e->u_nb[j]), gf.C, 0, c.w16(p.wmix), gf.C, 0, gf.M, gf.C, gf.C, SCOT_EPI_ADD_F32_BF16, nullptr,
               c.at<float>(e->u_x[j]), gf.C, c.at<bf16>(e->u_xb[j]), gf.C, skip[s - 1], gf.C));
       x = c.at<float>(e->u_x[j]);
       xb = c.at<bf16>(e->u_xb[j]);
     }
   }
+  RC(cnx_join_all(c));
   // ---- patch recovery (model.py:639-647) ----
   const int NR = d.num_out_channels * d.patch_size * d.patch_size;
   RC(scot_expand_bias_launch(c.p(e->rec_b), c.at<float>(e->rec_bias), NR, d.patch_size * d.patch_size, c.st));
@@ -773,6 +918,17 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
     }
   }
   e->join_pending[0] = e->join_pending[1] = false;
+  RC(cnx_side_init(e));
+  if (e->attn_split_ws < 0) {
+    const char* ev = getenv("SCOT_ATTN_BWD_SPLIT");
+    e->attn_split_ws = ev != nullptr ? atoi(ev) : 0;
+    if (e->attn_split_ws < 0) e->attn_split_ws = 0;
+  }
+  if (e->attn_split_ws > 0 && e->side3 == nullptr) {
+    SCOT_CHECK_CUDA(cudaStreamCreateWithFlags(&e->side3, cudaStreamNonBlocking));
+    SCOT_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_afork, cudaEventDisableTiming));
+    SCOT_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_ajoin, cudaEventDisableTiming));
+  }
   SCOT_CHECK_CUDA(cudaMemsetAsync(c.at<uint8_t>(e->dgrads_zero_begin), 0, e->dgrads_zero_bytes, c.st));
   // ---- loss + patch recovery backward ----
   float* dpred = c.at<float>(e->dpred);
@@ -820,35 +976,25 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
       RC(gemm(c, du, 2L * gc.C, 0, c.w16(p.wup), gc.C, 1, gc.M, gc.C, 2L * gc.C, SCOT_EPI_F32, nullptr,
               c.at<float>(e->gstage[s + 1]), gc.C));
     }
-  }
-  // ---- ConvNeXt backward on every skip ----
-  for (int s = 0; s < ns; ++s) {
-    const Geo& g = e->geo[s];
-    float* gr = c.at<float>(e->gstage[s]);
-    for (int k = d.skip_blocks[s] - 1; k >= 0; --k) {
-      const CnxP& p = e->cnx[s][k];
-      const CnxBuf& b = e->cbuf[s][k];
-      const float* blk_in = (k == 0) ? c.at<float>(e->ebuf[s].back().xout) : c.at<float>(e->cbuf[s][k - 1].out);
-      bf16* dzb = c.at<bf16>(e->dzb);
-      bf16* dh = c.at<bf16>(e->dh);
-      RC(scot_scale_add_bwd_launch(gr, c.at<bf16>(b.z2b), c.p(p.gamma), dzb, c.g(p.gamma), c.g(p.b2), g.M, g.C, c.st));
-      RC(gemm(c, dzb, g.C, 0, c.w16(p.w2), 4L * g.C, 1, g.M, 4L * g.C, g.C, SCOT_EPI_GELU_BWD, nullptr, dh, 4L * g.C, nullptr,
-              0, c.at<bf16>(b.h), 4L * g.C, c.g(p.b1)));
-      RC(gemm(c, dh, 4L * g.C, 0, c.w16(p.w1), g.C, 1, g.M, g.C, 4L * g.C, SCOT_EPI_F32, nullptr, c.at<float>(e->z32), g.C));
-      const ScotWgradProblem wg[2] = {
-          {dzb, g.C, c.at<bf16>(b.g), 4L * g.C, c.g(p.w2), 4L * g.C, g.M, g.C, 4 * g.C},  // pwconv2
-          {dh, 4L * g.C, c.at<bf16>(b.nb), g.C, c.g(p.w1), g.C, g.M, 4 * g.C, g.C},        // pwconv1
-      };
-      RC(scot_gemm_wgrad_group_launch(wg, 2, c.impl, c.st));
-      RC(norm_bwd(c, p.norm, c.at<float>(e->z32), c.at<bf16>(b.zhat), c.at<float>(b.rstd), c.at<float>(e->y32), 1,
-                  c.g(p.bdw), g.M, g.C, g.res * g.res, 0));
-      RC(scot_dwconv7_bwd_launch(blk_in, c.p(p.wdw), c.at<float>(e->y32), gr, gr, c.g(p.wdw), B, g.res, g.C, c.st));
+    if (cnx_on_side(e, s)) {
+      // gstage[s] now holds the gradient of the post-ConvNeXt skip and is not touched by the main stream until the
+      // encoder backward reaches stage s: the ConvNeXt backward runs beside the deeper stages
+      Ctx cs = c;
+      cs.st = e->side2;
+      RC(cnx_fork(c, s));
+      RC(cnx_bwd_stage(cs, s, gr, cnx_scratch(c, true)));
+      RC(cnx_mark_join(c, s));
     }
   }
+  // ---- ConvNeXt backward on every skip (those that did not run as a side branch above) ----
+  for (int s = 0; s < ns; ++s)
+    if (d.skip_blocks[s] > 0 && !cnx_on_side(e, s))
+      RC(cnx_bwd_stage(c, s, c.at<float>(e->gstage[s]), cnx_scratch(c, false)));
   // ---- encoder backward (coarsest stage first) ----
   for (int s = ns - 1; s >= 0; --s) {
     const Geo& g = e->geo[s];
     float* gr = c.at<float>(e->gstage[s]);
+    RC(cnx_join(c, s));  // ConvNeXt backward of this stage's skip (side branch) has updated gstage[s]
     if (s < ns - 1) {
       // merge backward: gstage[s+1] = grad wrt merge output
       const Geo& gn = e->geo[s + 1];
@@ -875,6 +1021,7 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
       RC(scot_merge_scatter_launch(c.at<float>(e->z32), gr, gr, B, g.res, g.C, c.st));
     }
   }
+  RC(cnx_join_all(c));
   // ---- embeddings backward ----
   {
     const int K0 = d.num_channels * d.patch_size * d.patch_size;

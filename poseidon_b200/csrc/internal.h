@@ -24,6 +24,15 @@ int scot_attn_bwd_launch(const void* qkv, const void* o, const void* d_o, const 
                          const float* alpha, void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha,
                          float* g_qbias, float* g_vbias, int batch, int res, int ws, int shift, int heads, int hd,
                          cudaStream_t st);
+// same, with the dk/dv kernel forked onto a second stream (events are recorded / waited inside; capturable)
+struct ScotAttnBwdFork {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
+int scot_attn_bwd_launch2(const void* qkv, const void* o, const void* d_o, const float* lse, const float* tab2,
+                          const float* alpha, void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha,
+                          float* g_qbias, float* g_vbias, int batch, int res, int ws, int shift, int heads, int hd,
+                          cudaStream_t st, const ScotAttnBwdFork* fk);
 // misc.cu
 int scot_cast_f32_bf16_launch(const float* in, void* out, long n, cudaStream_t st);
 int scot_expand_bias_launch(const float* bias, float* out, int n, int rep, cudaStream_t st);

@@ -3,6 +3,8 @@
 // ScOTPatchRecovery, layer-scale residual, casts and the (relative) Lp loss.
 // Reference call sites: scOT/model.py:295-310 (embed), :694-704 (merge order (0,0),(1,0),(0,1),(1,1)),
 // :198-217 (ConvNeXt), :639-647 (recovery), :1422-1484 (pixel_mask overwrite + loss).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -197,6 +199,72 @@ dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
         acc[k].y = fmaf(in[k + kx].y, w1, acc[k].y);
         acc[k].z = fmaf(in[k + kx].z, w2, acc[k].z);
         acc[k].w = fmaf(in[k + kx].w, w3, acc[k].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int xx = x0 + k;
+    if (xx >= res) break;
+    const long o = (((long)b * res + py) * res + xx) * C + c;
+    float4 v = acc[k];
+    if (add != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(add + o);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    *reinterpret_cast<float4*>(out + o) = v;
+  }
+}
+// Same computation with the filter staged in shared memory, transposed to [49][C + 4]: the four channels of a thread
+// are one conflict-free 128-bit LDS per tap. In dwconv7_kernel the 28 scalar weight loads per filter row have a
+// 196-float stride between lanes (one L1 wavefront per lane), which, not the FMAs or the activations, bounds it.
+template <bool FLIP>
+__global__ void __launch_bounds__(128)
+dwconv7s_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                const float* __restrict__ add, float* __restrict__ out, int B, int res, int C) {
+  extern __shared__ __align__(16) float sw[];  // [49][C + 4]
+  const int pitch = C + 4;
+  for (int k = threadIdx.x; k < 49 * C; k += blockDim.x) {
+    const int c = k / 49, tap = k - c * 49;
+    sw[(FLIP ? 48 - tap : tap) * pitch + c] = w[k];  // FLIP: tap (6-ky, 6-kx) is stored at (ky, kx)
+  }
+  __syncthreads();
+  const int c4n = C / 4, xg = (res + 7) / 8;
+  const long total = (long)B * res * xg * c4n;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = (int)(i % c4n);
+  long t = i / c4n;
+  const int gx = (int)(t % xg);
+  t /= xg;
+  const int py = (int)(t % res);
+  const int b = (int)(t / res);
+  const int c = c4 * 4, x0 = gx * 8;
+  float4 acc[8];
+  const float4 bz = bias != nullptr ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = bz;
+#pragma unroll 1
+  for (int ky = 0; ky < 7; ++ky) {
+    const int yy = py + ky - 3;
+    if (yy < 0 || yy >= res) continue;
+    float4 in[14];
+    const float* rowp = x + (((long)b * res + yy) * res) * C + c;
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      const int xx = x0 + k - 3;
+      in[k] = (xx >= 0 && xx < res) ? *reinterpret_cast<const float4*>(rowp + (long)xx * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* wrow = sw + (ky * 7) * pitch + c;
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const float4 w4 = *reinterpret_cast<const float4*>(wrow + kx * pitch);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[k].x = fmaf(in[k + kx].x, w4.x, acc[k].x);
+        acc[k].y = fmaf(in[k + kx].y, w4.y, acc[k].y);
+        acc[k].z = fmaf(in[k + kx].z, w4.z, acc[k].z);
+        acc[k].w = fmaf(in[k + kx].w, w4.w, acc[k].w);
       }
     }
   }
@@ -587,18 +655,39 @@ int scot_scale_add_bwd_launch(const float* g, const void* zb, const float* gamma
   SCOT_LAUNCH_CHECK();
   return 0;
 }
-int scot_dwconv7_fwd_launch(const float* x, const float* w, const float* bias, float* out, int B, int res, int C,
-                            cudaStream_t st) {
+// SCOT_DWCONV_SMEM=1: filter staged in shared memory (dwconv7s_kernel) when it fits comfortably (C <= 384)
+static bool dwconv_smem_enabled() {
+  const char* e = getenv("SCOT_DWCONV_SMEM");  // read per launch (not cached): lets one process compare both variants
+  return e != nullptr && e[0] == '1';
+}
+template <bool FLIP>
+static int launch_dwconv7(const float* x, const float* w, const float* bias, const float* add, float* out, int B, int res,
+                          int C, cudaStream_t st) {
   const long total = (long)B * res * ((res + 7) / 8) * (C / 4);
-  dwconv7_kernel<false><<<blocks_for(total, 128), 128, 0, st>>>(x, w, bias, nullptr, out, B, res, C);
+  const size_t smem = (size_t)49 * (C + 4) * sizeof(float);
+  if (dwconv_smem_enabled() && smem <= 80 * 1024) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      SCOT_CHECK_CUDA(cudaFuncSetAttribute(dwconv7s_kernel<FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+      attr_done = true;
+    }
+    dwconv7s_kernel<FLIP><<<blocks_for(total, 128), 128, smem, st>>>(x, w, bias, add, out, B, res, C);
+  } else {
+    dwconv7_kernel<FLIP><<<blocks_for(total, 128), 128, 0, st>>>(x, w, bias, add, out, B, res, C);
+  }
   SCOT_LAUNCH_CHECK();
   return 0;
 }
+int scot_dwconv7_fwd_launch(const float* x, const float* w, const float* bias, float* out, int B, int res, int C,
+                            cudaStream_t st) {
+  return launch_dwconv7<false>(x, w, bias, nullptr, out, B, res, C, st);
+}
 int scot_dwconv7_bwd_launch(const float* x, const float* w, const float* dout, const float* g_in, float* g_out, float* g_w,
                             int B, int res, int C, cudaStream_t st) {
-  const long total = (long)B * res * ((res + 7) / 8) * (C / 4);
-  dwconv7_kernel<true><<<blocks_for(total, 128), 128, 0, st>>>(dout, w, nullptr, g_in, g_out, B, res, C);
-  SCOT_LAUNCH_CHECK();
+  {
+    int rc = launch_dwconv7<true>(dout, w, nullptr, g_in, g_out, B, res, C, st);
+    if (rc) return rc;
+  }
   const int c4n = C / 4;
   SCOT_REQUIRE(c4n <= 256, "dwconv7: at most 1024 channels");
   // images per block so that ~2 blocks per SM exist for each of the 7 filter rows
