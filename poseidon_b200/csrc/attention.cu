@@ -10,6 +10,8 @@
 // Backward (derived in SURVEY.md appendix D) recomputes P flash-style from q,k and the saved row
 // log-sum-exp; nothing N x N is stored.  Tensor work uses warp-level mma.sync m16n8k16 (bf16, fp32
 // accumulate); a tcgen05 version of these kernels is the planned next step.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -244,6 +246,64 @@ cpb_bwd_pre_kernel(ScotCpbTable tab, const float* __restrict__ params, float* __
     const float sg = 1.0f / (1.0f + __expf(-t));
     dpre[idx] = dtab[idx] * 16.0f * sg * (1.0f - sg);
   }
+}
+
+// ---- "fast" variants (SCOT_CPB_FAST=1) ------------------------------------------------------------------------------
+// forward: one warp per table ROW r = (dy, dx): the 512 hidden activations are computed once and reused by all heads
+// (the kernel above recomputes them per (row, head) entry); same fma order per entry, so the table is bit-identical.
+__global__ void __launch_bounds__(256)
+cpb_fwd_rows_kernel(ScotCpbTable tab, const float* __restrict__ params, uint8_t* __restrict__ arena) {
+  const ScotCpbLayer L = tab.layer[blockIdx.y];
+  const int ws = L.ws, heads = L.heads;
+  const int side = 2 * ws - 1;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const float* w1 = params + L.w1;
+  const float* b1 = params + L.b1;
+  const float* w2 = params + L.w2;
+  const float* ls = params + L.ls;
+  float* tab2 = reinterpret_cast<float*>(arena + (size_t)L.tab2 * 256);
+  float* alpha = reinterpret_cast<float*>(arena + (size_t)L.alpha * 256);
+  if (blockIdx.x == 0 && threadIdx.x < heads) alpha[threadIdx.x] = __expf(fminf(ls[threadIdx.x], 4.605170185988092f));  // ln 100, HF:448
+  if (r >= side * side) return;
+  const float c0 = cpb_coord(r / side - (ws - 1), ws), c1 = cpb_coord(r % side - (ws - 1), ws);
+  float hid[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int j = lane + 32 * k;
+    hid[k] = fmaxf(fmaf(w1[2 * j], c0, fmaf(w1[2 * j + 1], c1, b1[j])), 0.f);
+  }
+  for (int h = 0; h < heads; ++h) {
+    const float* w2h = w2 + h * 512;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t = fmaf(w2h[lane + 32 * k], hid[k], t);
+    t = warp_sum(t);
+    if (lane == 0) tab2[r * heads + h] = 16.0f / (1.0f + __expf(-t)) * kLog2e;
+  }
+}
+// backward pre-pass without the MLP recomputation: the forward table holds tab2 = 16 sigmoid(t) log2(e), so
+// sigmoid(t) = tab2 / (16 log2 e) and dpre = dtab * 16 s (1 - s) is element-wise.
+__global__ void __launch_bounds__(256)
+cpb_bwd_pre_fast_kernel(ScotCpbTable tab, const float* __restrict__ params, float* __restrict__ grads,
+                        uint8_t* __restrict__ arena) {
+  const ScotCpbLayer L = tab.layer[blockIdx.y];
+  const int ws = L.ws, heads = L.heads;
+  const int side = 2 * ws - 1;
+  const int total = side * side * heads;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* ls = params + L.ls;
+  const float* tab2 = reinterpret_cast<const float*>(arena + (size_t)L.tab2 * 256);
+  const float* dtab = reinterpret_cast<const float*>(arena + (size_t)L.dtab * 256);
+  const float* dalpha = reinterpret_cast<const float*>(arena + (size_t)L.dalpha * 256);
+  float* dpre = reinterpret_cast<float*>(arena + (size_t)L.dpre * 256);
+  if (blockIdx.x == 0 && threadIdx.x < heads) {
+    const float v = ls[threadIdx.x];
+    if (v <= 4.605170185988092f) atomicAdd(grads + L.ls + threadIdx.x, dalpha[threadIdx.x] * __expf(v));
+  }
+  if (idx >= total) return;
+  const float sg = tab2[idx] * (1.0f / (16.0f * kLog2e));
+  dpre[idx] = dtab[idx] * 16.0f * sg * (1.0f - sg);
 }
 
 // one thread per hidden unit j, blockIdx.x splits the table rows; register accumulation, few atomics
@@ -1045,15 +1105,31 @@ size_t scot_attn_bwd_partial_bytes(int ws, int heads, int total_windows) {
   return 256;
 }
 
+// knobs of the position-bias kernels (read per launch so that one process can compare the variants)
+static bool cpb_fast_enabled() {
+  const char* e = getenv("SCOT_CPB_FAST");
+  return e != nullptr && e[0] == '1';
+}
+static int cpb_bwd_split() {
+  const char* e = getenv("SCOT_CPB_BWD_SPLIT");  // row splits (gridDim.x) of cpb_bwd_mlp_kernel: fewer = fewer atomics
+  const int v = e != nullptr ? atoi(e) : 16;
+  return v >= 1 && v <= 64 ? v : 16;
+}
+
 int scot_cpb_fwd_launch(const ScotCpbTable* tab, const float* params, void* arena, cudaStream_t st) {
   SCOT_REQUIRE(tab && params && arena && tab->n >= 1 && tab->n <= SCOT_CPB_MAX_LAYERS, "cpb_fwd: bad table");
-  int max_total = 0;
+  int max_total = 0, max_rows = 0;
   for (int i = 0; i < tab->n; ++i) {
-    const int t = (2 * tab->layer[i].ws - 1) * (2 * tab->layer[i].ws - 1) * tab->layer[i].heads;
+    const int rows = (2 * tab->layer[i].ws - 1) * (2 * tab->layer[i].ws - 1);
+    const int t = rows * tab->layer[i].heads;
     max_total = t > max_total ? t : max_total;
+    max_rows = rows > max_rows ? rows : max_rows;
     SCOT_REQUIRE(tab->layer[i].heads <= 32 && tab->layer[i].ws <= 16, "cpb: at most 32 heads / window 16");
   }
-  cpb_fwd_kernel<<<dim3(ceil_div(max_total, 8), tab->n), 256, 0, st>>>(*tab, params, (uint8_t*)arena);
+  if (cpb_fast_enabled())
+    cpb_fwd_rows_kernel<<<dim3(ceil_div(max_rows, 8), tab->n), 256, 0, st>>>(*tab, params, (uint8_t*)arena);
+  else
+    cpb_fwd_kernel<<<dim3(ceil_div(max_total, 8), tab->n), 256, 0, st>>>(*tab, params, (uint8_t*)arena);
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -1066,9 +1142,12 @@ int scot_cpb_bwd_launch(const ScotCpbTable* tab, const float* params, float* gra
     max_total = t > max_total ? t : max_total;
     SCOT_REQUIRE(tab->layer[i].heads <= 32 && tab->layer[i].ws <= 16, "cpb: at most 32 heads / window 16");
   }
-  cpb_bwd_pre_kernel<<<dim3(ceil_div(max_total, 8), tab->n), 256, 0, st>>>(*tab, params, grads, (uint8_t*)arena);
+  if (cpb_fast_enabled())
+    cpb_bwd_pre_fast_kernel<<<dim3(ceil_div(max_total, 256), tab->n), 256, 0, st>>>(*tab, params, grads, (uint8_t*)arena);
+  else
+    cpb_bwd_pre_kernel<<<dim3(ceil_div(max_total, 8), tab->n), 256, 0, st>>>(*tab, params, grads, (uint8_t*)arena);
   SCOT_LAUNCH_CHECK();
-  cpb_bwd_mlp_kernel<<<dim3(16, tab->n), 512, 0, st>>>(*tab, params, grads, (const uint8_t*)arena);
+  cpb_bwd_mlp_kernel<<<dim3(cpb_bwd_split(), tab->n), 512, 0, st>>>(*tab, params, grads, (const uint8_t*)arena);
   SCOT_LAUNCH_CHECK();
   return 0;
 }

@@ -215,31 +215,33 @@ dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
     *reinterpret_cast<float4*>(out + o) = v;
   }
 }
-// Same computation with the filter staged in shared memory, transposed to [49][C + 4]: the four channels of a thread
-// are one conflict-free 128-bit LDS per tap. In dwconv7_kernel the 28 scalar weight loads per filter row have a
+// Same computation with the filter staged in shared memory, transposed to [49][4*cq + 4]: the four channels of a
+// thread are one conflict-free 128-bit LDS per tap. In dwconv7_kernel the 28 scalar weight loads per filter row have a
 // 196-float stride between lanes (one L1 wavefront per lane), which, not the FMAs or the activations, bounds it.
+// blockIdx.y selects a chunk of cq channel quads (cq divides C/4, cq <= 32), so a block stages at most 128 channels.
 template <bool FLIP>
 __global__ void __launch_bounds__(128)
 dwconv7s_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                const float* __restrict__ add, float* __restrict__ out, int B, int res, int C) {
-  extern __shared__ __align__(16) float sw[];  // [49][C + 4]
-  const int pitch = C + 4;
-  for (int k = threadIdx.x; k < 49 * C; k += blockDim.x) {
-    const int c = k / 49, tap = k - c * 49;
-    sw[(FLIP ? 48 - tap : tap) * pitch + c] = w[k];  // FLIP: tap (6-ky, 6-kx) is stored at (ky, kx)
+                const float* __restrict__ add, float* __restrict__ out, int B, int res, int C, int cq) {
+  extern __shared__ __align__(16) float sw[];  // [49][4*cq + 4]
+  const int cc = 4 * cq, pitch = cc + 4;
+  const int cbase = blockIdx.y * cc;  // first channel of this block's chunk
+  for (int k = threadIdx.x; k < 49 * cc; k += blockDim.x) {
+    const int cl = k / 49, tap = k - cl * 49;
+    sw[(FLIP ? 48 - tap : tap) * pitch + cl] = w[(long)(cbase + cl) * 49 + tap];  // FLIP: tap (6-ky, 6-kx) stored at (ky, kx)
   }
   __syncthreads();
-  const int c4n = C / 4, xg = (res + 7) / 8;
-  const long total = (long)B * res * xg * c4n;
+  const int xg = (res + 7) / 8;
+  const long total = (long)B * res * xg * cq;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int c4 = (int)(i % c4n);
-  long t = i / c4n;
+  const int ql = (int)(i % cq);
+  long t = i / cq;
   const int gx = (int)(t % xg);
   t /= xg;
   const int py = (int)(t % res);
   const int b = (int)(t / res);
-  const int c = c4 * 4, x0 = gx * 8;
+  const int c = cbase + ql * 4, x0 = gx * 8;
   float4 acc[8];
   const float4 bz = bias != nullptr ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -255,7 +257,7 @@ dwconv7s_kernel(const float* __restrict__ x, const float* __restrict__ w, const 
       const int xx = x0 + k - 3;
       in[k] = (xx >= 0 && xx < res) ? *reinterpret_cast<const float4*>(rowp + (long)xx * C) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float* wrow = sw + (ky * 7) * pitch + c;
+    const float* wrow = sw + (ky * 7) * pitch + ql * 4;
 #pragma unroll
     for (int kx = 0; kx < 7; ++kx) {
       const float4 w4 = *reinterpret_cast<const float4*>(wrow + kx * pitch);
@@ -655,7 +657,7 @@ int scot_scale_add_bwd_launch(const float* g, const void* zb, const float* gamma
   SCOT_LAUNCH_CHECK();
   return 0;
 }
-// SCOT_DWCONV_SMEM=1: filter staged in shared memory (dwconv7s_kernel) when it fits comfortably (C <= 384)
+// SCOT_DWCONV_SMEM=1: filter staged in shared memory (dwconv7s_kernel)
 static bool dwconv_smem_enabled() {
   const char* e = getenv("SCOT_DWCONV_SMEM");  // read per launch (not cached): lets one process compare both variants
   return e != nullptr && e[0] == '1';
@@ -663,16 +665,15 @@ static bool dwconv_smem_enabled() {
 template <bool FLIP>
 static int launch_dwconv7(const float* x, const float* w, const float* bias, const float* add, float* out, int B, int res,
                           int C, cudaStream_t st) {
-  const long total = (long)B * res * ((res + 7) / 8) * (C / 4);
-  const size_t smem = (size_t)49 * (C + 4) * sizeof(float);
-  if (dwconv_smem_enabled() && smem <= 80 * 1024) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      SCOT_CHECK_CUDA(cudaFuncSetAttribute(dwconv7s_kernel<FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-      attr_done = true;
-    }
-    dwconv7s_kernel<FLIP><<<blocks_for(total, 128), 128, smem, st>>>(x, w, bias, add, out, B, res, C);
+  const int c4n = C / 4;
+  if (dwconv_smem_enabled()) {
+    int cq = c4n < 32 ? c4n : 32;  // channel quads per block: the largest divisor of C/4 that is <= 32
+    while (c4n % cq != 0) --cq;
+    const long total = (long)B * res * ((res + 7) / 8) * cq;
+    const size_t smem = (size_t)49 * (4 * cq + 4) * sizeof(float);  // <= 25.9 KB
+    dwconv7s_kernel<FLIP><<<dim3(blocks_for(total, 128), c4n / cq), 128, smem, st>>>(x, w, bias, add, out, B, res, C, cq);
   } else {
+    const long total = (long)B * res * ((res + 7) / 8) * c4n;
     dwconv7_kernel<FLIP><<<blocks_for(total, 128), 128, 0, st>>>(x, w, bias, add, out, B, res, C);
   }
   SCOT_LAUNCH_CHECK();

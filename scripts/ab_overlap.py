@@ -20,7 +20,7 @@ from poseidon_b200.runtime import GraphedTrainStep  # noqa: E402
 from poseidon_b200.scOT.model import ScOT, ScOTConfig  # noqa: E402
 
 OFF = {"SCOT_CNX_OVERLAP": "0", "SCOT_ATTN_BWD_SPLIT": "0", "SCOT_CLN_FWD_HOIST": "0", "SCOT_DWCONV_SMEM": "0",
-       "SCOT_ZERO_OVERLAP": "0"}
+       "SCOT_ZERO_OVERLAP": "0", "SCOT_CPB_FAST": "0", "SCOT_CPB_BWD_SPLIT": "16"}
 SETTINGS = [
     ("off", {}),
     ("hoist", {"SCOT_CLN_FWD_HOIST": "1"}),
@@ -28,8 +28,11 @@ SETTINGS = [
     ("cnx", {"SCOT_CNX_OVERLAP": "1"}),
     ("attn8", {"SCOT_ATTN_BWD_SPLIT": "8"}),
     ("zero", {"SCOT_ZERO_OVERLAP": "1"}),
-    ("all8", {"SCOT_ZERO_OVERLAP": "1", "SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "8", "SCOT_CLN_FWD_HOIST": "1", "SCOT_DWCONV_SMEM": "1"}),
-    ("all16", {"SCOT_ZERO_OVERLAP": "1", "SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "16", "SCOT_CLN_FWD_HOIST": "1", "SCOT_DWCONV_SMEM": "1"}),
+    ("cpbfast", {"SCOT_CPB_FAST": "1"}),
+    ("cpbsplit4", {"SCOT_CPB_BWD_SPLIT": "4"}),
+    ("cpbsplit8", {"SCOT_CPB_BWD_SPLIT": "8"}),
+    ("all8", {"SCOT_CPB_FAST": "1", "SCOT_CPB_BWD_SPLIT": "8", "SCOT_ZERO_OVERLAP": "1", "SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "8", "SCOT_CLN_FWD_HOIST": "1", "SCOT_DWCONV_SMEM": "1"}),
+    ("all16", {"SCOT_CPB_FAST": "1", "SCOT_CPB_BWD_SPLIT": "4", "SCOT_ZERO_OVERLAP": "1", "SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "16", "SCOT_CLN_FWD_HOIST": "1", "SCOT_DWCONV_SMEM": "1"}),
 ]
 
 

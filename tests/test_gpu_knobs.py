@@ -5,7 +5,8 @@ third stream, gradient memset beside the forward pass) and alternative kernels f
 with hoisted loads, depthwise 7x7 with the filter in shared memory). Each computes exactly the same arithmetic in the
 same order as the in-line path, so the prediction must be BIT-IDENTICAL and the gradients equal up to the reordering
 of fp32 atomics. Checked on a small model that has every block type (shifted windows, ConvNeXt skips at two stages,
-merging / unmerging, conditioned norms), eagerly and through the CUDA-graph step.
+merging / unmerging, conditioned norms), eagerly and through the CUDA-graph step. The position-bias knobs (hidden
+layer shared across heads; sigmoid taken from the forward table in backward; fewer row splits) follow the same rule.
 """
 import os
 
@@ -16,7 +17,8 @@ from oracle.weights import make_inputs, make_weights
 
 pytestmark = pytest.mark.gpu
 
-KNOBS = ["SCOT_CNX_OVERLAP", "SCOT_ATTN_BWD_SPLIT", "SCOT_CLN_FWD_HOIST", "SCOT_DWCONV_SMEM", "SCOT_ZERO_OVERLAP"]
+KNOBS = {"SCOT_CNX_OVERLAP": "0", "SCOT_ATTN_BWD_SPLIT": "0", "SCOT_CLN_FWD_HOIST": "0", "SCOT_DWCONV_SMEM": "0",
+         "SCOT_ZERO_OVERLAP": "0", "SCOT_CPB_FAST": "0", "SCOT_CPB_BWD_SPLIT": "16"}
 CFG = dict(image_size=64, patch_size=4, num_channels=3, num_out_channels=3, embed_dim=32, depths=[2, 2, 2],
            num_heads=[2, 4, 8], skip_connections=[2, 1, 0], window_size=8, mlp_ratio=4.0, drop_path_rate=0.0,
            use_conditioning=True, p=1, channel_slice_list_normalized_loss=[0, 1, 3], residual_model="convnext")
@@ -28,8 +30,7 @@ def run(env, use_graph, batch=4):
 
     old = {k: os.environ.get(k) for k in KNOBS}
     try:
-        for k in KNOBS:
-            os.environ[k] = "0"
+        os.environ.update(KNOBS)
         os.environ.update(env)
         cfg = ScOTConfig(**CFG)
         model = ScOT(cfg)
@@ -65,9 +66,11 @@ def baseline():
     {"SCOT_CLN_FWD_HOIST": "1"},
     {"SCOT_DWCONV_SMEM": "1"},
     {"SCOT_ZERO_OVERLAP": "1"},
+    {"SCOT_CPB_FAST": "1"},
+    {"SCOT_CPB_BWD_SPLIT": "4"},
     {"SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "16", "SCOT_CLN_FWD_HOIST": "1", "SCOT_DWCONV_SMEM": "1",
-     "SCOT_ZERO_OVERLAP": "1"},
-], ids=["cnx", "attn", "hoist", "dwsmem", "zero", "all"])
+     "SCOT_ZERO_OVERLAP": "1", "SCOT_CPB_FAST": "1", "SCOT_CPB_BWD_SPLIT": "8"},
+], ids=["cnx", "attn", "hoist", "dwsmem", "zero", "cpbfast", "cpbsplit", "all"])
 def test_knob_is_result_neutral(baseline, env, use_graph):
     pred0, loss0, g0 = baseline
     for pred, loss, g in run(env, use_graph):
