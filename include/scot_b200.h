@@ -106,7 +106,8 @@ int scot_cln_bwd(const float* dy, const void* zhat, const float* rstd, const flo
 typedef struct ScotCpbLayer {
   int w1, b1, w2, ls;            /* continuous_position_bias_mlp.0.{weight,bias}, .2.weight, logit_scale */
   int tab2, alpha;               /* forward outputs: [(2ws-1)^2, heads] and [heads] floats */
-  int dtab, dalpha, dpre;        /* backward: inputs dtab/dalpha (from scot_attn_bwd), scratch dpre [(2ws-1)^2*heads] */
+  int dtab, dalpha, dpre;        /* backward: inputs dtab/dalpha (from scot_attn_bwd), scratch dpre [(2ws-1)^2*heads];
+                                  * scot_cpb_bwd also reads tab2 as left by scot_cpb_fwd (sigmoid = tab2 / (16 log2 e)) */
   short ws, heads;
 } ScotCpbLayer;
 typedef struct ScotCpbTable {

@@ -183,76 +183,13 @@ __device__ __forceinline__ float cpb_coord(int i, int ws) {
   return s * log2f(fabsf(x) + 1.0f) / 3.0f;
 }
 
-// All attention layers of the model are handled by ONE launch each (blockIdx.y = layer): the per-layer work is a
-// few thousand 512-term dot products, far too small to amortise a launch of its own.
-__device__ __forceinline__ float cpb_table_value(const float* __restrict__ w1, const float* __restrict__ b1,
-                                                 const float* __restrict__ w2h, float c0, float c1, int lane) {
-  // one warp per table entry: lanes split the 512 hidden units
-  float t = 0.f;
-#pragma unroll 4
-  for (int j = lane; j < 512; j += 32) {
-    const float hid = fmaxf(fmaf(w1[2 * j], c0, fmaf(w1[2 * j + 1], c1, b1[j])), 0.f);
-    t = fmaf(w2h[j], hid, t);
-  }
-  return warp_sum(t);
-}
-
+// All attention layers of the model are handled by ONE launch each (blockIdx.y = layer): the per-layer work is a few
+// thousand 512-term dot products, far too small to amortise a launch of its own.
+// forward: one warp per table ROW r = (dy, dx): the 512 hidden activations are computed once (16 per lane) and reused
+// by all heads. (Round-1 history: a warp per (row, head) entry that recomputed the hidden layer per head and launched
+// ~46 k mostly empty blocks took 120 us; this one 50 us, bit-identical table.)
 __global__ void __launch_bounds__(256)
 cpb_fwd_kernel(ScotCpbTable tab, const float* __restrict__ params, uint8_t* __restrict__ arena) {
-  const ScotCpbLayer L = tab.layer[blockIdx.y];
-  const int ws = L.ws, heads = L.heads;
-  const int side = 2 * ws - 1;
-  const int total = side * side * heads;
-  const int lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const float* w1 = params + L.w1;
-  const float* b1 = params + L.b1;
-  const float* w2 = params + L.w2;
-  const float* ls = params + L.ls;
-  float* tab2 = reinterpret_cast<float*>(arena + (size_t)L.tab2 * 256);
-  float* alpha = reinterpret_cast<float*>(arena + (size_t)L.alpha * 256);
-  if (blockIdx.x == 0 && threadIdx.x < heads) alpha[threadIdx.x] = __expf(fminf(ls[threadIdx.x], 4.605170185988092f));  // ln 100, HF:448
-  if (idx >= total) return;
-  const int r = idx / heads, h = idx - r * heads;
-  const float c0 = cpb_coord(r / side - (ws - 1), ws), c1 = cpb_coord(r % side - (ws - 1), ws);
-  const float t = cpb_table_value(w1, b1, w2 + h * 512, c0, c1, lane);
-  if (lane == 0) tab2[idx] = 16.0f / (1.0f + __expf(-t)) * kLog2e;
-}
-
-// dtab[r,h] = d loss / d (16*sigmoid(t)) ; produces dpre = dtab * 16 * s * (1-s) and d logit_scale
-__global__ void __launch_bounds__(256)
-cpb_bwd_pre_kernel(ScotCpbTable tab, const float* __restrict__ params, float* __restrict__ grads,
-                   uint8_t* __restrict__ arena) {
-  const ScotCpbLayer L = tab.layer[blockIdx.y];
-  const int ws = L.ws, heads = L.heads;
-  const int side = 2 * ws - 1;
-  const int total = side * side * heads;
-  const int lane = threadIdx.x & 31;
-  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const float* ls = params + L.ls;
-  const float* dtab = reinterpret_cast<const float*>(arena + (size_t)L.dtab * 256);
-  const float* dalpha = reinterpret_cast<const float*>(arena + (size_t)L.dalpha * 256);
-  float* dpre = reinterpret_cast<float*>(arena + (size_t)L.dpre * 256);
-  if (blockIdx.x == 0 && threadIdx.x < heads) {
-    const float v = ls[threadIdx.x];
-    // d/dls exp(min(ls, ln100)); torch.clamp(max=) passes the gradient where ls <= max
-    if (v <= 4.605170185988092f) atomicAdd(grads + L.ls + threadIdx.x, dalpha[threadIdx.x] * __expf(v));
-  }
-  if (idx >= total) return;
-  const int r = idx / heads, h = idx - r * heads;
-  const float c0 = cpb_coord(r / side - (ws - 1), ws), c1 = cpb_coord(r % side - (ws - 1), ws);
-  const float t = cpb_table_value(params + L.w1, params + L.b1, params + L.w2 + h * 512, c0, c1, lane);
-  if (lane == 0) {
-    const float sg = 1.0f / (1.0f + __expf(-t));
-    dpre[idx] = dtab[idx] * 16.0f * sg * (1.0f - sg);
-  }
-}
-
-// ---- "fast" variants (SCOT_CPB_FAST=1) ------------------------------------------------------------------------------
-// forward: one warp per table ROW r = (dy, dx): the 512 hidden activations are computed once and reused by all heads
-// (the kernel above recomputes them per (row, head) entry); same fma order per entry, so the table is bit-identical.
-__global__ void __launch_bounds__(256)
-cpb_fwd_rows_kernel(ScotCpbTable tab, const float* __restrict__ params, uint8_t* __restrict__ arena) {
   const ScotCpbLayer L = tab.layer[blockIdx.y];
   const int ws = L.ws, heads = L.heads;
   const int side = 2 * ws - 1;
@@ -282,10 +219,11 @@ cpb_fwd_rows_kernel(ScotCpbTable tab, const float* __restrict__ params, uint8_t*
     if (lane == 0) tab2[r * heads + h] = 16.0f / (1.0f + __expf(-t)) * kLog2e;
   }
 }
-// backward pre-pass without the MLP recomputation: the forward table holds tab2 = 16 sigmoid(t) log2(e), so
-// sigmoid(t) = tab2 / (16 log2 e) and dpre = dtab * 16 s (1 - s) is element-wise.
+// dtab[r,h] = d loss / d (16*sigmoid(t)) ; produces dpre = dtab * 16 * s * (1-s) and d logit_scale. No MLP
+// recomputation: the forward table holds tab2 = 16 sigmoid(t) log2(e), so sigmoid(t) = tab2 / (16 log2 e) and the
+// pre-pass is element-wise (5 us instead of 114 us for the 64 layers of Poseidon-B).
 __global__ void __launch_bounds__(256)
-cpb_bwd_pre_fast_kernel(ScotCpbTable tab, const float* __restrict__ params, float* __restrict__ grads,
+cpb_bwd_pre_kernel(ScotCpbTable tab, const float* __restrict__ params, float* __restrict__ grads,
                         uint8_t* __restrict__ arena) {
   const ScotCpbLayer L = tab.layer[blockIdx.y];
   const int ws = L.ws, heads = L.heads;
@@ -1105,17 +1043,6 @@ size_t scot_attn_bwd_partial_bytes(int ws, int heads, int total_windows) {
   return 256;
 }
 
-// knobs of the position-bias kernels (read per launch so that one process can compare the variants)
-static bool cpb_fast_enabled() {
-  const char* e = getenv("SCOT_CPB_FAST");
-  return e != nullptr && e[0] == '1';
-}
-static int cpb_bwd_split() {
-  const char* e = getenv("SCOT_CPB_BWD_SPLIT");  // row splits (gridDim.x) of cpb_bwd_mlp_kernel: fewer = fewer atomics
-  const int v = e != nullptr ? atoi(e) : 16;
-  return v >= 1 && v <= 64 ? v : 16;
-}
-
 int scot_cpb_fwd_launch(const ScotCpbTable* tab, const float* params, void* arena, cudaStream_t st) {
   SCOT_REQUIRE(tab && params && arena && tab->n >= 1 && tab->n <= SCOT_CPB_MAX_LAYERS, "cpb_fwd: bad table");
   int max_total = 0, max_rows = 0;
@@ -1126,10 +1053,8 @@ int scot_cpb_fwd_launch(const ScotCpbTable* tab, const float* params, void* aren
     max_rows = rows > max_rows ? rows : max_rows;
     SCOT_REQUIRE(tab->layer[i].heads <= 32 && tab->layer[i].ws <= 16, "cpb: at most 32 heads / window 16");
   }
-  if (cpb_fast_enabled())
-    cpb_fwd_rows_kernel<<<dim3(ceil_div(max_rows, 8), tab->n), 256, 0, st>>>(*tab, params, (uint8_t*)arena);
-  else
-    cpb_fwd_kernel<<<dim3(ceil_div(max_total, 8), tab->n), 256, 0, st>>>(*tab, params, (uint8_t*)arena);
+  (void)max_total;
+  cpb_fwd_kernel<<<dim3(ceil_div(max_rows, 8), tab->n), 256, 0, st>>>(*tab, params, (uint8_t*)arena);
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -1142,12 +1067,10 @@ int scot_cpb_bwd_launch(const ScotCpbTable* tab, const float* params, float* gra
     max_total = t > max_total ? t : max_total;
     SCOT_REQUIRE(tab->layer[i].heads <= 32 && tab->layer[i].ws <= 16, "cpb: at most 32 heads / window 16");
   }
-  if (cpb_fast_enabled())
-    cpb_bwd_pre_fast_kernel<<<dim3(ceil_div(max_total, 256), tab->n), 256, 0, st>>>(*tab, params, grads, (uint8_t*)arena);
-  else
-    cpb_bwd_pre_kernel<<<dim3(ceil_div(max_total, 8), tab->n), 256, 0, st>>>(*tab, params, grads, (uint8_t*)arena);
+  cpb_bwd_pre_kernel<<<dim3(ceil_div(max_total, 256), tab->n), 256, 0, st>>>(*tab, params, grads, (uint8_t*)arena);
   SCOT_LAUNCH_CHECK();
-  cpb_bwd_mlp_kernel<<<dim3(cpb_bwd_split(), tab->n), 512, 0, st>>>(*tab, params, grads, (const uint8_t*)arena);
+  // 16 row splits per layer: 4 and 8 (fewer atomics, longer row loops) measured the same on B200
+  cpb_bwd_mlp_kernel<<<dim3(16, tab->n), 512, 0, st>>>(*tab, params, grads, (const uint8_t*)arena);
   SCOT_LAUNCH_CHECK();
   return 0;
 }

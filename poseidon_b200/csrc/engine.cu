@@ -628,8 +628,8 @@ int cnx_bwd_stage(const Ctx& c, int s, float* gr, const CnxScratch& sc) {
 // Side-branch plumbing: fork e->side2 from the main stream, run `fn` there, record the join event of stage s.
 int cnx_side_init(ScotEngine* e) {
   if (e->cnx_overlap < 0) {
-    const char* ev = getenv("SCOT_CNX_OVERLAP");
-    e->cnx_overlap = (ev != nullptr && ev[0] == '1') ? 1 : 0;
+    const char* ev = getenv("SCOT_CNX_OVERLAP");  // default on; SCOT_CNX_OVERLAP=0 runs the blocks in line (A/B, tests)
+    e->cnx_overlap = (ev != nullptr && ev[0] == '0') ? 0 : 1;
   }
   if (e->cnx_overlap && e->z32C == 0 && e->dhC == 0) e->cnx_overlap = 0;  // nothing to overlap
   if (e->cnx_overlap && e->side2 == nullptr) {
@@ -920,8 +920,8 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
   e->join_pending[0] = e->join_pending[1] = false;
   RC(cnx_side_init(e));
   if (e->attn_split_ws < 0) {
-    const char* ev = getenv("SCOT_ATTN_BWD_SPLIT");
-    e->attn_split_ws = ev != nullptr ? atoi(ev) : 0;
+    const char* ev = getenv("SCOT_ATTN_BWD_SPLIT");  // default: every window size; 0 = both kernels on the main stream
+    e->attn_split_ws = ev != nullptr ? atoi(ev) : 16;
     if (e->attn_split_ws < 0) e->attn_split_ws = 0;
   }
   if (e->attn_split_ws > 0 && e->side3 == nullptr) {

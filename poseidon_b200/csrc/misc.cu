@@ -3,8 +3,6 @@
 // ScOTPatchRecovery, layer-scale residual, casts and the (relative) Lp loss.
 // Reference call sites: scOT/model.py:295-310 (embed), :694-704 (merge order (0,0),(1,0),(0,1),(1,1)),
 // :198-217 (ConvNeXt), :639-647 (recovery), :1422-1484 (pixel_mask overwrite + loss).
-#include <cstdlib>
-
 #include "common.cuh"
 #include "internal.h"
 
@@ -199,74 +197,6 @@ dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
         acc[k].y = fmaf(in[k + kx].y, w1, acc[k].y);
         acc[k].z = fmaf(in[k + kx].z, w2, acc[k].z);
         acc[k].w = fmaf(in[k + kx].w, w3, acc[k].w);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int xx = x0 + k;
-    if (xx >= res) break;
-    const long o = (((long)b * res + py) * res + xx) * C + c;
-    float4 v = acc[k];
-    if (add != nullptr) {
-      const float4 a = *reinterpret_cast<const float4*>(add + o);
-      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-    }
-    *reinterpret_cast<float4*>(out + o) = v;
-  }
-}
-// Same computation with the filter staged in shared memory, transposed to [49][4*cq + 4]: the four channels of a
-// thread are one conflict-free 128-bit LDS per tap. In dwconv7_kernel the 28 scalar weight loads per filter row have a
-// 196-float stride between lanes (one L1 wavefront per lane), which, not the FMAs or the activations, bounds it.
-// blockIdx.y selects a chunk of cq channel quads (cq divides C/4, cq <= 32), so a block stages at most 128 channels.
-template <bool FLIP>
-__global__ void __launch_bounds__(128)
-dwconv7s_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                const float* __restrict__ add, float* __restrict__ out, int B, int res, int C, int cq) {
-  extern __shared__ __align__(16) float sw[];  // [49][4*cq + 4]
-  const int cc = 4 * cq, pitch = cc + 4;
-  const int cbase = blockIdx.y * cc;  // first channel of this block's chunk
-  for (int k = threadIdx.x; k < 49 * cc; k += blockDim.x) {
-    const int cl = k / 49, tap = k - cl * 49;
-    sw[(FLIP ? 48 - tap : tap) * pitch + cl] = w[(long)(cbase + cl) * 49 + tap];  // FLIP: tap (6-ky, 6-kx) stored at (ky, kx)
-  }
-  __syncthreads();
-  const int xg = (res + 7) / 8;
-  const long total = (long)B * res * xg * cq;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int ql = (int)(i % cq);
-  long t = i / cq;
-  const int gx = (int)(t % xg);
-  t /= xg;
-  const int py = (int)(t % res);
-  const int b = (int)(t / res);
-  const int c = cbase + ql * 4, x0 = gx * 8;
-  float4 acc[8];
-  const float4 bz = bias != nullptr ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = bz;
-#pragma unroll 1
-  for (int ky = 0; ky < 7; ++ky) {
-    const int yy = py + ky - 3;
-    if (yy < 0 || yy >= res) continue;
-    float4 in[14];
-    const float* rowp = x + (((long)b * res + yy) * res) * C + c;
-#pragma unroll
-    for (int k = 0; k < 14; ++k) {
-      const int xx = x0 + k - 3;
-      in[k] = (xx >= 0 && xx < res) ? *reinterpret_cast<const float4*>(rowp + (long)xx * C) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const float* wrow = sw + (ky * 7) * pitch + ql * 4;
-#pragma unroll
-    for (int kx = 0; kx < 7; ++kx) {
-      const float4 w4 = *reinterpret_cast<const float4*>(wrow + kx * pitch);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        acc[k].x = fmaf(in[k + kx].x, w4.x, acc[k].x);
-        acc[k].y = fmaf(in[k + kx].y, w4.y, acc[k].y);
-        acc[k].z = fmaf(in[k + kx].z, w4.z, acc[k].z);
-        acc[k].w = fmaf(in[k + kx].w, w4.w, acc[k].w);
       }
     }
   }
@@ -657,38 +587,18 @@ int scot_scale_add_bwd_launch(const float* g, const void* zb, const float* gamma
   SCOT_LAUNCH_CHECK();
   return 0;
 }
-// SCOT_DWCONV_SMEM=1: filter staged in shared memory (dwconv7s_kernel)
-static bool dwconv_smem_enabled() {
-  const char* e = getenv("SCOT_DWCONV_SMEM");  // read per launch (not cached): lets one process compare both variants
-  return e != nullptr && e[0] == '1';
-}
-template <bool FLIP>
-static int launch_dwconv7(const float* x, const float* w, const float* bias, const float* add, float* out, int B, int res,
-                          int C, cudaStream_t st) {
-  const int c4n = C / 4;
-  if (dwconv_smem_enabled()) {
-    int cq = c4n < 32 ? c4n : 32;  // channel quads per block: the largest divisor of C/4 that is <= 32
-    while (c4n % cq != 0) --cq;
-    const long total = (long)B * res * ((res + 7) / 8) * cq;
-    const size_t smem = (size_t)49 * (4 * cq + 4) * sizeof(float);  // <= 25.9 KB
-    dwconv7s_kernel<FLIP><<<dim3(blocks_for(total, 128), c4n / cq), 128, smem, st>>>(x, w, bias, add, out, B, res, C, cq);
-  } else {
-    const long total = (long)B * res * ((res + 7) / 8) * c4n;
-    dwconv7_kernel<FLIP><<<blocks_for(total, 128), 128, 0, st>>>(x, w, bias, add, out, B, res, C);
-  }
+int scot_dwconv7_fwd_launch(const float* x, const float* w, const float* bias, float* out, int B, int res, int C,
+                            cudaStream_t st) {
+  const long total = (long)B * res * ((res + 7) / 8) * (C / 4);
+  dwconv7_kernel<false><<<blocks_for(total, 128), 128, 0, st>>>(x, w, bias, nullptr, out, B, res, C);
   SCOT_LAUNCH_CHECK();
   return 0;
 }
-int scot_dwconv7_fwd_launch(const float* x, const float* w, const float* bias, float* out, int B, int res, int C,
-                            cudaStream_t st) {
-  return launch_dwconv7<false>(x, w, bias, nullptr, out, B, res, C, st);
-}
 int scot_dwconv7_bwd_launch(const float* x, const float* w, const float* dout, const float* g_in, float* g_out, float* g_w,
                             int B, int res, int C, cudaStream_t st) {
-  {
-    int rc = launch_dwconv7<true>(dout, w, nullptr, g_in, g_out, B, res, C, st);
-    if (rc) return rc;
-  }
+  const long total = (long)B * res * ((res + 7) / 8) * (C / 4);
+  dwconv7_kernel<true><<<blocks_for(total, 128), 128, 0, st>>>(dout, w, nullptr, g_in, g_out, B, res, C);
+  SCOT_LAUNCH_CHECK();
   const int c4n = C / 4;
   SCOT_REQUIRE(c4n <= 256, "dwconv7: at most 1024 channels");
   // images per block so that ~2 blocks per SM exist for each of the 7 filter rows

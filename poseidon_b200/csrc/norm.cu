@@ -44,12 +44,7 @@ __device__ __forceinline__ long unmerge_row(long r_in, int res) {
   return (b * (2 * res) + 2 * i + a) * (long)(2 * res) + 2 * j + c;
 }
 
-// HOIST: every global load is issued before the first store (the residual row together with the input row, ahead
-// of the reductions), and all stores come last. In the plain variant each of the V column groups does store(zhat) ->
-// load(scale, residual) -> store(x): the stores may alias the loads as far as the compiler knows, so the kernel pays V
-// dependent memory round trips per row — at the deep stages (C = 384 / 768, a few thousand rows) that latency chain is
-// most of its run time.
-template <int LPR, int V, bool HOIST>
+template <int LPR, int V>
 __global__ void __launch_bounds__(256) cln_fwd_kernel(ClnFwdArgs p) {
   pdl_launch_dependents();
   pdl_wait();
@@ -62,27 +57,15 @@ __global__ void __launch_bounds__(256) cln_fwd_kernel(ClnFwdArgs p) {
   const unsigned mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
   const int nvec = p.C >> 2;
   float4 v[V];
-  float4 res[HOIST ? V : 1];
-  long r_out_h = r_in;
-  float t_h = 0.f;
-  if constexpr (HOIST) {
-    r_out_h = p.perm_res > 0 ? unmerge_row(r_in, p.perm_res) : r_in;
-    if (p.time != nullptr) t_h = p.time[r_out_h / p.rows_per_sample];
-  }
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int cv = sl + i * LPR;
     if (cv < nvec) {
       v[i] = *reinterpret_cast<const float4*>(p.z + r_in * p.C + cv * 4);
-      if constexpr (HOIST) {
-        res[i] = p.residual != nullptr ? *reinterpret_cast<const float4*>(p.residual + r_out_h * p.C + cv * 4)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if constexpr (HOIST) res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 #pragma unroll
@@ -100,49 +83,6 @@ __global__ void __launch_bounds__(256) cln_fwd_kernel(ClnFwdArgs p) {
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(mask, q, o);
   const float rstd = rsqrtf(q / (float)p.C + p.eps);
-  if constexpr (HOIST) {
-    const long r_out = r_out_h;
-    const float t = t_h;
-    // phase 1: loads + math (v <- normalised row, res <- output row)
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int cv = sl + i * LPR;
-      if (cv >= nvec) continue;
-      const int c0 = cv * 4;
-      const float4 ab = *reinterpret_cast<const float4*>(p.ab + c0);
-      const float4 cb = *reinterpret_cast<const float4*>(p.cb + c0);
-      float sc[4] = {ab.x, ab.y, ab.z, ab.w}, sh[4] = {cb.x, cb.y, cb.z, cb.w};
-      if (p.aw != nullptr) {
-        const float4 aw = *reinterpret_cast<const float4*>(p.aw + c0);
-        const float4 cw = *reinterpret_cast<const float4*>(p.cw + c0);
-        sc[0] = fmaf(aw.x, t, sc[0]); sc[1] = fmaf(aw.y, t, sc[1]); sc[2] = fmaf(aw.z, t, sc[2]); sc[3] = fmaf(aw.w, t, sc[3]);
-        sh[0] = fmaf(cw.x, t, sh[0]); sh[1] = fmaf(cw.y, t, sh[1]); sh[2] = fmaf(cw.z, t, sh[2]); sh[3] = fmaf(cw.w, t, sh[3]);
-      }
-      v[i] = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
-      // same operation order as the plain variant: y = fma(scale, zhat, shift); y += residual
-      float y0 = fmaf(sc[0], v[i].x, sh[0]), y1 = fmaf(sc[1], v[i].y, sh[1]);
-      float y2 = fmaf(sc[2], v[i].z, sh[2]), y3 = fmaf(sc[3], v[i].w, sh[3]);
-      if (p.residual != nullptr) {
-        y0 += res[i].x; y1 += res[i].y; y2 += res[i].z; y3 += res[i].w;
-      }
-      res[i] = make_float4(y0, y1, y2, y3);
-    }
-    // phase 2: stores
-    if (sl == 0 && p.rstd != nullptr) p.rstd[r_out] = rstd;
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const int cv = sl + i * LPR;
-      if (cv >= nvec) continue;
-      const int c0 = cv * 4;
-      if (p.zhat != nullptr)
-        *reinterpret_cast<uint2*>(p.zhat + r_out * p.C + c0) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
-      if (p.x_out != nullptr) *reinterpret_cast<float4*>(p.x_out + r_out * p.C + c0) = res[i];
-      if (p.xb_out != nullptr)
-        *reinterpret_cast<uint2*>(p.xb_out + r_out * p.C + c0) =
-            make_uint2(pack_bf16x2(res[i].x, res[i].y), pack_bf16x2(res[i].z, res[i].w));
-    }
-    return;
-  }
   const long r_out = p.perm_res > 0 ? unmerge_row(r_in, p.perm_res) : r_in;
   const float t = p.time != nullptr ? p.time[r_out / p.rows_per_sample] : 0.f;
   if (sl == 0 && p.rstd != nullptr) p.rstd[r_out] = rstd;
@@ -370,20 +310,12 @@ __global__ void __launch_bounds__(256, (V <= 3 ? 2 : 1)) cln_bwd_kernel(ClnBwdAr
   }
 }
 
-// SCOT_CLN_FWD_HOIST=1 selects the load-hoisting variant (A/B knob)
-bool cln_fwd_hoist_enabled() {
-  const char* e = getenv("SCOT_CLN_FWD_HOIST");  // read per launch (not cached): lets one process compare both variants
-  return e != nullptr && e[0] == '1';
-}
 template <int LPR, int V>
 int launch_fwd(const ClnFwdArgs& a, cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
   const int warps = 8;
   const long blocks = (a.rows + (long)warps * RPW - 1) / ((long)warps * RPW);
-  if (cln_fwd_hoist_enabled() && V <= 6)  // wider rows (C = 1536) would spill
-    SCOT_CHECK_CUDA(scot_launch_pdl(cln_fwd_kernel<LPR, V, (V <= 6)>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, a));
-  else
-    SCOT_CHECK_CUDA(scot_launch_pdl(cln_fwd_kernel<LPR, V, false>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, a));
+  SCOT_CHECK_CUDA(scot_launch_pdl(cln_fwd_kernel<LPR, V>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, a));
   SCOT_LAUNCH_CHECK();
   return 0;
 }

@@ -7,7 +7,6 @@ SURVEY.md §2 row 11); here the gradients already live in one flat buffer, so a 
 """
 from __future__ import annotations
 
-import os
 from typing import Optional
 
 import torch
@@ -47,7 +46,6 @@ class GraphedTrainStep:
         self.graph = None
         self.optimizer = optimizer  # e.g. poseidon_b200.optim.FlatAdamW: fused clip + AdamW on the flat buffers
         self._impl = model.gemm_impl
-        self._zero_stream = None
         # bind .grad to the flat views once; the graph zeroes and refills the same memory every step
         for p, gv in zip(st["plist"], st["gviews"]):
             p.grad = gv
@@ -56,22 +54,9 @@ class GraphedTrainStep:
 
     def _body(self):
         st = self.st
-        # SCOT_ZERO_OVERLAP=1: the 4 B/parameter gradient memset runs on a side stream beside the forward pass (the
-        # gradients are first touched by the backward pass); fork / join through stream events, capturable
-        overlap_zero = os.environ.get("SCOT_ZERO_OVERLAP", "0") == "1"
-        if overlap_zero:
-            cur = torch.cuda.current_stream(self.device)
-            if self._zero_stream is None:
-                self._zero_stream = torch.cuda.Stream(device=self.device)
-            self._zero_stream.wait_stream(cur)
-            with torch.cuda.stream(self._zero_stream):
-                st["gflat"].zero_()
-        else:
-            st["gflat"].zero_()
+        st["gflat"].zero_()
         st["engine"].forward(st["flat"], st["arena"], self.x, self.t, self.y, self.mask, 1 if self.mask is not None else 0,
                              self.pred, self.loss, self._impl)
-        if overlap_zero:
-            cur.wait_stream(self._zero_stream)
         st["engine"].backward(st["flat"], st["gflat"], st["arena"], self.gscale, None, self._impl)
 
     def _capture(self):

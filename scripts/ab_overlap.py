@@ -4,7 +4,7 @@
 
 Builds one engine per knob setting (the knobs are read from the environment when an engine first runs), feeds all of
 them the same seeded batch and weights, and compares prediction (must be bit-identical: the forward pass has no
-atomics), loss and the flat gradient (atomics reorder: ~1e-6 relative) against the all-off engine; then times CUDA-graph
+atomics), loss and the flat gradient (atomics reorder: ~1e-6 relative) against the in-line engine; then times CUDA-graph
 replays of zero-grad + forward + backward.
 """
 import json
@@ -19,20 +19,13 @@ from bench import model_config, realistic_init_  # noqa: E402
 from poseidon_b200.runtime import GraphedTrainStep  # noqa: E402
 from poseidon_b200.scOT.model import ScOT, ScOTConfig  # noqa: E402
 
-OFF = {"SCOT_CNX_OVERLAP": "0", "SCOT_ATTN_BWD_SPLIT": "0", "SCOT_CLN_FWD_HOIST": "0", "SCOT_DWCONV_SMEM": "0",
-       "SCOT_ZERO_OVERLAP": "0", "SCOT_CPB_FAST": "0", "SCOT_CPB_BWD_SPLIT": "16"}
+OFF = {"SCOT_CNX_OVERLAP": "0", "SCOT_ATTN_BWD_SPLIT": "0"}
 SETTINGS = [
-    ("off", {}),
-    ("hoist", {"SCOT_CLN_FWD_HOIST": "1"}),
-    ("dwsmem", {"SCOT_DWCONV_SMEM": "1"}),
+    ("inline", {}),
     ("cnx", {"SCOT_CNX_OVERLAP": "1"}),
     ("attn8", {"SCOT_ATTN_BWD_SPLIT": "8"}),
-    ("zero", {"SCOT_ZERO_OVERLAP": "1"}),
-    ("cpbfast", {"SCOT_CPB_FAST": "1"}),
-    ("cpbsplit4", {"SCOT_CPB_BWD_SPLIT": "4"}),
-    ("cpbsplit8", {"SCOT_CPB_BWD_SPLIT": "8"}),
-    ("all8", {"SCOT_CPB_FAST": "1", "SCOT_CPB_BWD_SPLIT": "8", "SCOT_ZERO_OVERLAP": "1", "SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "8", "SCOT_CLN_FWD_HOIST": "1", "SCOT_DWCONV_SMEM": "1"}),
-    ("all16", {"SCOT_CPB_FAST": "1", "SCOT_CPB_BWD_SPLIT": "4", "SCOT_ZERO_OVERLAP": "1", "SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "16", "SCOT_CLN_FWD_HOIST": "1", "SCOT_DWCONV_SMEM": "1"}),
+    ("attn16", {"SCOT_ATTN_BWD_SPLIT": "16"}),
+    ("defaults", {"SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "16"}),
 ]
 
 
