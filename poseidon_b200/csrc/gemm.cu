@@ -633,6 +633,275 @@ gemm_async_epi_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
 }
 
 // =================================================================================================
+// "v2" of the async-epilogue kernel (SCOT_GEMM_ASYNC_V2=1; NOT yet validated on hardware — round-2 candidate).
+//
+// Motivation (profiles/r01_ncu_full_summary.md, stall sampling of the kernel above): the epilogue is a serial chain per
+// CTA. 28 % (bf16) / 16 % (GELU) of the samples wait behind `cp.async.bulk.wait_group.read 0`, i.e. for the previous
+// tile's TMA store to read its staging tile (the store queues behind the operand loads in the TMA unit), and all the
+// epilogue arithmetic sits AFTER that wait. Changes, same producer / MMA warps and barriers otherwise:
+//   * every mode: tcgen05.ld + all arithmetic first (results packed as bf16 in registers, accumulator buffer released),
+//     THEN the wait for the staging tile, then only the 128-bit shared-memory stores;
+//   * BF16 mode: two staging tiles used alternately, `wait_group.read 1` (the previous store may still be reading);
+//   * GELU_BWD mode: no staging tile at all — the product is written in place into the aux-ring stage that delivered the
+//     saved gelu' tile (same 128 x 64 bf16 128B-swizzled layout) and stored from there; the stage goes back to the
+//     producer when that store has read it (aux_empty: one arrival by the issuer instead of 256 by the readers). This
+//     frees 16 KB: three operand stages instead of two;
+//   * GELU mode: bias kept in shared memory (one broadcast LDS.128 per four columns) instead of 32 registers per thread,
+//     so that both packed outputs (32 registers) fit next to the accumulator row without spilling at 2 CTAs / SM.
+// =================================================================================================
+template <int BMN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
+  constexpr bool kHasAux = (MODE == SCOT_EPI_GELU_BWD);
+  constexpr int kNumOut = (MODE == SCOT_EPI_GELU) ? 2 : 1;
+  constexpr int kOutBufs = (MODE == SCOT_EPI_BF16) ? 2 : (MODE == SCOT_EPI_GELU ? 1 : 0);  // staging tiles per output
+  constexpr int kAccCols = 64, kTmemCols = 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = empty_bar + 8;        // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint64_t* aux_full_bar = tmem_empty_bar + 2;    // [2]
+  uint64_t* aux_empty_bar = aux_full_bar + 2;     // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux_empty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + 512);                    // [64] bias of the current column block
+  uint8_t* tiles = smem + 1024;
+  uint8_t* aux_s = tiles + (size_t)num_stages * kAStageBytes;             // [2][16 KB] (GELU_BWD only; doubles as staging)
+  uint8_t* out_s = aux_s + (kHasAux ? 2 * kOutTileBytes : 0);             // [kOutBufs][kNumOut][16 KB]
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = ga.total_tiles;
+  const int tiles_per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = min(total_tiles, t_begin + tiles_per_cta);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&ga.tmA);
+    tma_prefetch_desc(&ga.tmB);
+    tma_prefetch_desc(&ga.tmOut1);
+    if (kHasAux) tma_prefetch_desc(&ga.tmAux);
+    if (kNumOut == 2 || MODE != SCOT_EPI_GELU) tma_prefetch_desc(&ga.tmOut0);
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], EPI_THREADS);
+      mbar_init(&aux_full_bar[b], 1);
+      mbar_init(&aux_empty_bar[b], 1);  // v2: released by the store issuer once the in-place result has been stored
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (as in v1) ------------------------------
+    if (lane == 0) {
+      int it = 0, lt = 0;
+      for (int t = t_begin; t < t_end; ++t, ++lt) {
+        const int cb = t / ga.tiles_m;  // m fastest
+        const int m0 = (t - cb * ga.tiles_m) * BM, n0 = cb * ABN;
+        if constexpr (kHasAux) {
+          const int as = lt & 1;
+          mbar_wait_backoff(&aux_empty_bar[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&aux_full_bar[as], kOutTileBytes);
+          tma_load_2d(aux_s + as * kOutTileBytes, &ga.tmAux, &aux_full_bar[as], n0, m0);
+        }
+        for (int kb = 0; kb < ga.kblocks; ++kb, ++it) {
+          const int s = it % num_stages;
+          const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
+          mbar_wait_backoff(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], kAStageBytes);
+          uint8_t* sa = tiles + (size_t)s * kAStageBytes;
+          uint8_t* sb = sa + BM * BK * 2;
+          const int k0 = kb * BK;
+          tma_load_2d(sa, &ga.tmA, &full_bar[s], k0, m0);
+          if constexpr (BMN == 0) tma_load_2d(sb, &ga.tmB, &full_bar[s], k0, n0);
+          else tma_load_2d(sb, &ga.tmB, &full_bar[s], n0, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (as in v1) ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, ABN, 0, BMN);
+      int it = 0, lt = 0;
+      for (int t = t_begin; t < t_end; ++t, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait_backoff(&tmem_empty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * kAccCols);
+        for (int i = 0; i < ga.kblocks; ++i, ++it) {
+          const int s = it % num_stages;
+          const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
+          mbar_wait_backoff(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)s * kAStageBytes);
+          const uint32_t sb = sa + BM * BK * 2;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = (BMN == 0) ? umma_smem_desc(sb + k * 32, 16, 1024)
+                                           : umma_smem_desc(sb + k * 2048, BK * 128, 1024);
+            umma_bf16(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (8 warps) ------------------------------
+    const int ew = warp - 2;             // 0..7
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = ew >> 2;            // which 32-column half of the tile this warp converts
+    const int et = ew * 32 + lane;       // 0..255
+    const int row = q * 32 + lane;       // accumulator row (TMEM lane) of this thread
+    const bool issuer = (et == 0);       // issues / tracks the bulk stores
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t row_off = (uint32_t)row * 128u;
+    float cs0 = 0.f, cs1 = 0.f;          // GELU_BWD: running sums of columns 2*(et&31), +1 over rows (et>>5)*16..+15
+    int bias_cb = -1;
+    int lt = 0;
+    for (int t = t_begin; t < t_end; ++t, ++lt) {
+      const int cb = t / ga.tiles_m;
+      const int m0 = (t - cb * ga.tiles_m) * BM, n0 = cb * ABN;
+      const int buf = lt & 1;
+      if constexpr (MODE != SCOT_EPI_GELU_BWD) {
+        if (cb != bias_cb) {  // block-uniform: every epilogue thread sees the same tile sequence
+          bias_cb = cb;
+          asm volatile("bar.sync 3, %0;" ::"n"(EPI_THREADS) : "memory");  // readers of the previous column block's bias are done
+          if (et < ABN) bias_s[et] = (ga.bias != nullptr && n0 + et < ga.N) ? __ldg(ga.bias + n0 + et) : 0.f;
+          asm volatile("bar.sync 3, %0;" ::"n"(EPI_THREADS) : "memory");
+        }
+      }
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+      float v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t)(buf * kAccCols + half * 32) + ((uint32_t)(q * 32) << 16), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[buf]);  // the MMA warp may start the tile after next in this accumulator
+      // ---- arithmetic first: results as packed bf16 in registers ----
+      uint32_t o0[16];
+      uint32_t o1[(MODE == SCOT_EPI_GELU) ? 16 : 1];
+      uint32_t stage_base;  // shared-memory address of this thread's row in the tile that will be stored
+      if constexpr (MODE == SCOT_EPI_GELU) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = b4[j];
+          const float xs[4] = {v[4 * j] + bb.x, v[4 * j + 1] + bb.y, v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w};
+          float c[4], p[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gelu_parts(xs[k], c[k], p[k]);
+          o0[2 * j] = pack_bf16x2(fmaf(xs[0], p[0], c[0]), fmaf(xs[1], p[1], c[1]));      // gelu'
+          o0[2 * j + 1] = pack_bf16x2(fmaf(xs[2], p[2], c[2]), fmaf(xs[3], p[3], c[3]));
+          o1[2 * j] = pack_bf16x2(xs[0] * c[0], xs[1] * c[1]);                             // gelu
+          o1[2 * j + 1] = pack_bf16x2(xs[2] * c[2], xs[3] * c[3]);
+        }
+        stage_base = smem_u32(out_s) + row_off;
+      } else if constexpr (MODE == SCOT_EPI_BF16) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = b4[j];
+          o0[2 * j] = pack_bf16x2(v[4 * j] + bb.x, v[4 * j + 1] + bb.y);
+          o0[2 * j + 1] = pack_bf16x2(v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+        }
+        stage_base = smem_u32(out_s) + (uint32_t)(buf * kOutTileBytes) + row_off;
+      } else {  // GELU_BWD: dh = acc * gelu'(h); gelu'(h) sits in aux stage `buf`, the product replaces it in place
+        mbar_wait(&aux_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
+        stage_base = smem_u32(aux_s) + (uint32_t)(buf * kOutTileBytes) + row_off;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 a = lds128(stage_base + ((((uint32_t)(half * 4 + j)) ^ swz) << 4));
+          const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 g = unpack_bf16x2(w[k]);
+            o0[4 * j + k] = pack_bf16x2(v[j * 8 + 2 * k] * g.x, v[j * 8 + 2 * k + 1] * g.y);
+          }
+        }
+      }
+      // ---- now the tile that receives the results must be free ----
+      if constexpr (MODE == SCOT_EPI_BF16) {
+        if (issuer) bulk_wait_read<1>();   // the store issued two tiles ago used this buffer; the last one may still read
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      } else if constexpr (MODE == SCOT_EPI_GELU) {
+        if (issuer) bulk_wait_read<0>();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      }
+      // GELU_BWD: every thread rewrites exactly the 64 bytes it has just read; no other thread touches them before bar.sync 2
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = (((uint32_t)(half * 4 + j)) ^ swz) << 4;
+        sts128(stage_base + off, o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
+        if constexpr (MODE == SCOT_EPI_GELU)
+          sts128(stage_base + kOutTileBytes + off, o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+      if (issuer) {
+        if constexpr (MODE == SCOT_EPI_GELU) {
+          if (ga.has_out0) tma_store_2d(&ga.tmOut0, out_s, n0, m0);
+          tma_store_2d(&ga.tmOut1, out_s + kOutTileBytes, n0, m0);
+          bulk_commit();
+        } else if constexpr (MODE == SCOT_EPI_BF16) {
+          tma_store_2d(&ga.tmOut0, out_s + buf * kOutTileBytes, n0, m0);
+          bulk_commit();
+        } else {
+          tma_store_2d(&ga.tmOut0, aux_s + buf * kOutTileBytes, n0, m0);
+          bulk_commit();
+          // the store issued for the PREVIOUS tile (other aux stage) has read its source by now or we wait for it: hand
+          // that stage back to the producer
+          if (lt > 0) {
+            bulk_wait_read<1>();
+            mbar_arrive(&aux_empty_bar[buf ^ 1]);
+          }
+        }
+      }
+      if constexpr (MODE == SCOT_EPI_GELU_BWD) {
+        // bias gradient: column sums of the bf16 values just staged (rows >= M hold zeros: their A rows were zero-filled)
+        const int cp = et & 31, rg = et >> 5;
+        const uint32_t chunk = (uint32_t)(cp >> 2), word = (uint32_t)(cp & 3) * 4;
+        const uint32_t obase = smem_u32(aux_s) + (uint32_t)(buf * kOutTileBytes) + word;
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+          const int r = rg * 16 + rr;
+          const float2 f = unpack_bf16x2(lds32(obase + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+          cs0 += f.x;
+          cs1 += f.y;
+        }
+        const bool last_of_col = (t + 1 >= t_end) || ((t + 1) / ga.tiles_m != cb);
+        if (last_of_col && ga.colsum != nullptr) {
+          const int c = n0 + 2 * cp;
+          if (c < ga.N) atomicAdd(ga.colsum + c, cs0);
+          if (c + 1 < ga.N) atomicAdd(ga.colsum + c + 1, cs1);
+          cs0 = cs1 = 0.f;
+        }
+      }
+    }
+    if (issuer) bulk_wait<0>();  // all stores of this CTA are performed before the grid can complete
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// =================================================================================================
 // SIMT reference kernel (bring-up / cross-check path; same epilogue semantics, fp32 FMA on CUDA cores)
 // =================================================================================================
 template <int MODE>
@@ -797,7 +1066,13 @@ bool async_epi_enabled() {
   return v == 1;
 }
 
-template <int BMN, int MODE>
+// SCOT_GEMM_ASYNC_V2=1 selects gemm_async_epi2_kernel (round-2 candidate, see its header)
+bool async_v2_enabled() {
+  const char* e = getenv("SCOT_GEMM_ASYNC_V2");
+  return e != nullptr && e[0] == '1';
+}
+
+template <int BMN, int MODE, bool V2 = false>
 int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
                  cudaStream_t stream) {
   AsyncArgs ga;
@@ -832,14 +1107,16 @@ int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N,
   ga.bias = ep.bias;
   ga.colsum = ep.colsum;
   ga.has_out0 = ep.out0 != nullptr;
-  const size_t fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + (MODE == SCOT_EPI_GELU_BWD ? 2 * kOutTileBytes : 0) +
-                       (MODE == SCOT_EPI_GELU ? 2 : 1) * kOutTileBytes;
+  // staging tiles: v1 one per output (+ the aux ring for GELU_BWD); v2: two for BF16, the aux ring alone for GELU_BWD
+  const size_t staging = V2 ? (MODE == SCOT_EPI_GELU ? 2 : (MODE == SCOT_EPI_BF16 ? 2 : 0)) * (size_t)kOutTileBytes
+                            : (MODE == SCOT_EPI_GELU ? 2 : 1) * (size_t)kOutTileBytes;
+  const size_t fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + (MODE == SCOT_EPI_GELU_BWD ? 2 * kOutTileBytes : 0) + staging;
   const size_t budget = (size_t)(227 * 1024) / 2 - 1024;
   int stages = (int)((budget - fixed) / kAStageBytes);
   if (stages > 4) stages = 4;
   SCOT_REQUIRE(stages >= 2, "gemm(async epilogue): shared memory budget");
   const size_t smem = fixed + (size_t)stages * kAStageBytes;
-  auto kern = gemm_async_epi_kernel<BMN, MODE>;
+  auto kern = V2 ? gemm_async_epi2_kernel<BMN, MODE> : gemm_async_epi_kernel<BMN, MODE>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     SCOT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 / 2));
@@ -862,8 +1139,10 @@ int dispatch_bn(const void* A, long lda, const void* B, long ldb, int M, int N, 
   if constexpr (AMN == 0 && (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_GELU_BWD || MODE == SCOT_EPI_BF16)) {
     if (async_epi_enabled() && tma_ok(ep.out0, ep.ld0) && tma_ok(ep.out1, ep.ld1) && tma_ok(ep.aux, ep.ldaux) &&
         (MODE != SCOT_EPI_GELU || ep.out1 != nullptr) && (MODE != SCOT_EPI_GELU_BWD || ep.aux != nullptr) &&
-        (BMN == 0 || N % 8 == 0))
+        (BMN == 0 || N % 8 == 0)) {
+      if (async_v2_enabled()) return launch_async<BMN, MODE, true>(A, lda, B, ldb, M, N, K, ep, stream);
       return launch_async<BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
+    }
   }
   // epilogue-bound modes (two bf16 streams / transcendental math): 128 x 64 tiles, two resident CTAs per SM
   if constexpr (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_GELU_BWD) {

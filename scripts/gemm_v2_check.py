@@ -1,0 +1,81 @@
+"""Round-2 bring-up of gemm_async_epi2_kernel (SCOT_GEMM_ASYNC_V2=1): bit-compare against the validated v1 kernel on
+the three bf16-output epilogue modes and time both. Run under a timeout — v2 has never executed on hardware:
+
+    timeout 120 python scripts/gemm_v2_check.py
+
+The knob is read per launch, so one process can alternate between the two kernels. Expected: outputs bit-identical
+(same arithmetic, only the order of waits / the staging buffers differ), bias-gradient column sums equal up to the
+order of the fp32 atomics.
+"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from poseidon_b200 import _lib as L  # noqa: E402
+
+dev = "cuda"
+SHAPES = [(65536, 384, 96), (16384, 768, 192), (4096, 1536, 384), (1024, 3072, 768), (1000, 192, 96), (65536, 288, 96)]
+
+
+def run(v2, fn):
+    os.environ["SCOT_GEMM_ASYNC_V2"] = "1" if v2 else "0"
+    fn()
+    torch.cuda.synchronize()
+
+
+def timeit(v2, fn, n=20):
+    os.environ["SCOT_GEMM_ASYNC_V2"] = "1" if v2 else "0"
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+def main():
+    torch.manual_seed(0)
+    report = []
+    for M, N, K in SHAPES:
+        A = torch.randn(M, K, device=dev).bfloat16()
+        B = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+        Bt = (torch.randn(K, N, device=dev) / K ** 0.5).bfloat16()  # MN-major B operand of a dgrad
+        bias = torch.randn(N, device=dev)
+        aux = torch.randn(M, N, device=dev).bfloat16()
+        outs = {}
+        for v2 in (False, True):
+            o_bf = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+            o_bfT = torch.zeros_like(o_bf)
+            o_g0, o_g1 = torch.zeros_like(o_bf), torch.zeros_like(o_bf)
+            o_bw = torch.zeros_like(o_bf)
+            cs = torch.zeros(N, device=dev)
+            run(v2, lambda: L.gemm(A, B, M, N, K, mode=L.EPI_BF16, bias=bias, out0=o_bf))
+            run(v2, lambda: L.gemm(A, Bt, M, N, K, b_mn=True, mode=L.EPI_BF16, out0=o_bfT))
+            run(v2, lambda: L.gemm(A, B, M, N, K, mode=L.EPI_GELU, bias=bias, out0=o_g0, out1=o_g1))
+            run(v2, lambda: L.gemm(A, Bt, M, N, K, b_mn=True, mode=L.EPI_GELU_BWD, out0=o_bw, aux=aux, colsum=cs))
+            t = {
+                "bf16": timeit(v2, lambda: L.gemm(A, B, M, N, K, mode=L.EPI_BF16, bias=bias, out0=o_bf)),
+                "gelu": timeit(v2, lambda: L.gemm(A, B, M, N, K, mode=L.EPI_GELU, bias=bias, out0=o_g0, out1=o_g1)),
+                "gelu_bwd": timeit(v2, lambda: L.gemm(A, Bt, M, N, K, b_mn=True, mode=L.EPI_GELU_BWD, out0=o_bw, aux=aux)),
+            }
+            outs[v2] = (o_bf, o_bfT, o_g0, o_g1, o_bw, cs, t)
+        a, b = outs[False], outs[True]
+        rec = {"shape": [M, N, K],
+               "equal": {n: bool(torch.equal(x, y)) for n, x, y in zip(("bf16", "bf16_T", "gelu_d", "gelu", "gelu_bwd"), a[:5], b[:5])},
+               "colsum_rel": float((a[5] - b[5]).norm() / (a[5].norm() + 1e-30)),
+               "us_v1": {k: round(v, 2) for k, v in a[6].items()}, "us_v2": {k: round(v, 2) for k, v in b[6].items()}}
+        print(json.dumps(rec), flush=True)
+        report.append(rec)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(report, open("gpurun_out/gemm_v2_check.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
