@@ -654,7 +654,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
   constexpr bool kHasAux = (MODE == SCOT_EPI_GELU_BWD);
   constexpr int kNumOut = (MODE == SCOT_EPI_GELU) ? 2 : 1;
-  constexpr int kOutBufs = (MODE == SCOT_EPI_BF16) ? 2 : (MODE == SCOT_EPI_GELU ? 1 : 0);  // staging tiles per output
+  constexpr int kOutBufs = (MODE == SCOT_EPI_BF16) ? 2 : (MODE == SCOT_EPI_GELU_BWD ? 0 : 1);  // staging tiles per output
+  static_assert(kOutBufs >= 0, "");
   constexpr int kAccCols = 64, kTmemCols = 128;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -776,7 +777,7 @@ gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
       const int cb = t / ga.tiles_m;
       const int m0 = (t - cb * ga.tiles_m) * BM, n0 = cb * ABN;
       const int buf = lt & 1;
-      if constexpr (MODE != SCOT_EPI_GELU_BWD) {
+      if constexpr (MODE != SCOT_EPI_GELU_BWD && MODE != SCOT_EPI_RMW_F32) {
         if (cb != bias_cb) {  // block-uniform: every epilogue thread sees the same tile sequence
           bias_cb = cb;
           asm volatile("bar.sync 3, %0;" ::"n"(EPI_THREADS) : "memory");  // readers of the previous column block's bias are done
@@ -819,6 +820,17 @@ gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
           o0[2 * j + 1] = pack_bf16x2(v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
         }
         stage_base = smem_u32(out_s) + (uint32_t)(buf * kOutTileBytes) + row_off;
+      } else if constexpr (MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32) {
+        // fp32 output: this thread's 32 columns are one 128-byte row of its half's 128 x 32 fp32 box (128B swizzle)
+        if constexpr (MODE == SCOT_EPI_F32) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + half * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+          }
+        }
+        stage_base = smem_u32(out_s) + (uint32_t)(half * kOutTileBytes) + row_off;
       } else {  // GELU_BWD: dh = acc * gelu'(h); gelu'(h) sits in aux stage `buf`, the product replaces it in place
         mbar_wait(&aux_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
         stage_base = smem_u32(aux_s) + (uint32_t)(buf * kOutTileBytes) + row_off;
@@ -837,17 +849,24 @@ gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
       if constexpr (MODE == SCOT_EPI_BF16) {
         if (issuer) bulk_wait_read<1>();   // the store issued two tiles ago used this buffer; the last one may still read
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-      } else if constexpr (MODE == SCOT_EPI_GELU) {
+      } else if constexpr (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32) {
         if (issuer) bulk_wait_read<0>();
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       }
       // GELU_BWD: every thread rewrites exactly the 64 bytes it has just read; no other thread touches them before bar.sync 2
+      if constexpr (MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t off = (((uint32_t)(half * 4 + j)) ^ swz) << 4;
-        sts128(stage_base + off, o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
-        if constexpr (MODE == SCOT_EPI_GELU)
-          sts128(stage_base + kOutTileBytes + off, o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+        for (int j = 0; j < 8; ++j)  // eight 16-byte chunks = the whole 128-byte row of this half
+          sts128(stage_base + ((((uint32_t)j) ^ swz) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                 __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = (((uint32_t)(half * 4 + j)) ^ swz) << 4;
+          sts128(stage_base + off, o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
+          if constexpr (MODE == SCOT_EPI_GELU)
+            sts128(stage_base + kOutTileBytes + off, o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+        }
       }
       fence_proxy_async_smem();
       asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
@@ -858,6 +877,14 @@ gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
           bulk_commit();
         } else if constexpr (MODE == SCOT_EPI_BF16) {
           tma_store_2d(&ga.tmOut0, out_s + buf * kOutTileBytes, n0, m0);
+          bulk_commit();
+        } else if constexpr (MODE == SCOT_EPI_F32) {
+          tma_store_2d(&ga.tmOut0, out_s, n0, m0);  // fp32 tensor map, box {32, 128}: one store per column half
+          if (n0 + 32 < ga.N) tma_store_2d(&ga.tmOut0, out_s + kOutTileBytes, n0 + 32, m0);
+          bulk_commit();
+        } else if constexpr (MODE == SCOT_EPI_RMW_F32) {
+          tma_reduce_add_2d(&ga.tmOut0, out_s, n0, m0);  // out += tile, the fp32 add is performed by the L2
+          if (n0 + 32 < ga.N) tma_reduce_add_2d(&ga.tmOut0, out_s + kOutTileBytes, n0 + 32, m0);
           bulk_commit();
         } else {
           tma_store_2d(&ga.tmOut0, aux_s + buf * kOutTileBytes, n0, m0);
@@ -966,6 +993,20 @@ int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, 
   SCOT_REQUIRE(r == CUDA_SUCCESS,
                "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, ptr,
                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+  return 0;
+}
+
+// fp32 row-major tensor [outer, inner], box {32, 128} (one 128-byte swizzle atom wide)
+int make_tmap_f32(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SCOT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(fp32) failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu", (int)r, ptr,
+               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
   return 0;
 }
 
@@ -1089,6 +1130,10 @@ int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N,
     }
     rc = make_tmap(&ga.tmOut1, ep.out1, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld1, 64, BM);
     if (rc) return rc;
+  } else if (MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32) {
+    rc = make_tmap_f32(&ga.tmOut0, ep.out0, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld0);
+    if (rc) return rc;
+    ga.tmOut1 = ga.tmOut0;
   } else {
     rc = make_tmap(&ga.tmOut0, ep.out0, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld0, 64, BM);
     if (rc) return rc;
@@ -1108,15 +1153,17 @@ int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N,
   ga.colsum = ep.colsum;
   ga.has_out0 = ep.out0 != nullptr;
   // staging tiles: v1 one per output (+ the aux ring for GELU_BWD); v2: two for BF16, the aux ring alone for GELU_BWD
-  const size_t staging = V2 ? (MODE == SCOT_EPI_GELU ? 2 : (MODE == SCOT_EPI_BF16 ? 2 : 0)) * (size_t)kOutTileBytes
-                            : (MODE == SCOT_EPI_GELU ? 2 : 1) * (size_t)kOutTileBytes;
+  const size_t staging = V2 ? (MODE == SCOT_EPI_GELU_BWD ? 0 : 2) * (size_t)kOutTileBytes  // GELU: two outputs; BF16: two
+                            : (MODE == SCOT_EPI_GELU ? 2 : 1) * (size_t)kOutTileBytes;          // buffers; fp32: two halves
   const size_t fixed = 1024 /*align slack*/ + 1024 /*barriers*/ + (MODE == SCOT_EPI_GELU_BWD ? 2 * kOutTileBytes : 0) + staging;
   const size_t budget = (size_t)(227 * 1024) / 2 - 1024;
   int stages = (int)((budget - fixed) / kAStageBytes);
   if (stages > 4) stages = 4;
   SCOT_REQUIRE(stages >= 2, "gemm(async epilogue): shared memory budget");
   const size_t smem = fixed + (size_t)stages * kAStageBytes;
-  auto kern = V2 ? gemm_async_epi2_kernel<BMN, MODE> : gemm_async_epi_kernel<BMN, MODE>;
+  void (*kern)(AsyncArgs, int);
+  if constexpr (V2) kern = gemm_async_epi2_kernel<BMN, MODE>;
+  else kern = gemm_async_epi_kernel<BMN, MODE>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     SCOT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 / 2));
@@ -1143,6 +1190,13 @@ int dispatch_bn(const void* A, long lda, const void* B, long ldb, int M, int N, 
       if (async_v2_enabled()) return launch_async<BMN, MODE, true>(A, lda, B, ldb, M, N, K, ep, stream);
       return launch_async<BMN, MODE>(A, lda, B, ldb, M, N, K, ep, stream);
     }
+  }
+  // v2 only: fp32-output modes through the async epilogue (TMA store / TMA reduce-add). `+=` only where gemm_tc_kernel
+  // would not split K (large token counts): the async kernel has no split reduction.
+  if constexpr (AMN == 0 && (MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32)) {
+    if (async_v2_enabled() && (((uintptr_t)ep.out0) & 15) == 0 && ep.ld0 % 4 == 0 && (BMN == 0 || N % 8 == 0) &&
+        (MODE == SCOT_EPI_F32 || ceil_div(M, BM) * ceil_div(N, 128) >= 2 * g_num_sms))
+      return launch_async<BMN, MODE, true>(A, lda, B, ldb, M, N, K, ep, stream);
   }
   // epilogue-bound modes (two bf16 streams / transcendental math): 128 x 64 tiles, two resident CTAs per SM
   if constexpr (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_GELU_BWD) {

@@ -1,5 +1,5 @@
 """Round-2 bring-up of gemm_async_epi2_kernel (SCOT_GEMM_ASYNC_V2=1): bit-compare against the validated v1 kernel on
-the three bf16-output epilogue modes and time both. Run under a timeout — v2 has never executed on hardware:
+the bf16-output epilogue modes (v1 = gemm_async_epi_kernel) and the fp32-output modes (v1 = gemm_tc_kernel) and time both. Run under a timeout — v2 has never executed on hardware:
 
     timeout 120 python scripts/gemm_v2_check.py
 
@@ -49,6 +49,7 @@ def main():
         Bt = (torch.randn(K, N, device=dev) / K ** 0.5).bfloat16()  # MN-major B operand of a dgrad
         bias = torch.randn(N, device=dev)
         aux = torch.randn(M, N, device=dev).bfloat16()
+        acc0 = torch.randn(M, N, device=dev)  # initial content of the `+=` target
         outs = {}
         for v2 in (False, True):
             o_bf = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
@@ -60,17 +61,23 @@ def main():
             run(v2, lambda: L.gemm(A, Bt, M, N, K, b_mn=True, mode=L.EPI_BF16, out0=o_bfT))
             run(v2, lambda: L.gemm(A, B, M, N, K, mode=L.EPI_GELU, bias=bias, out0=o_g0, out1=o_g1))
             run(v2, lambda: L.gemm(A, Bt, M, N, K, b_mn=True, mode=L.EPI_GELU_BWD, out0=o_bw, aux=aux, colsum=cs))
+            o_f = torch.zeros(M, N, device=dev)
+            o_rmw = acc0.clone()
+            run(v2, lambda: L.gemm(A, B, M, N, K, mode=L.EPI_F32, bias=bias, out0=o_f))
+            run(v2, lambda: L.gemm(A, Bt, M, N, K, b_mn=True, mode=L.EPI_RMW_F32, out0=o_rmw))
             t = {
                 "bf16": timeit(v2, lambda: L.gemm(A, B, M, N, K, mode=L.EPI_BF16, bias=bias, out0=o_bf)),
                 "gelu": timeit(v2, lambda: L.gemm(A, B, M, N, K, mode=L.EPI_GELU, bias=bias, out0=o_g0, out1=o_g1)),
                 "gelu_bwd": timeit(v2, lambda: L.gemm(A, Bt, M, N, K, b_mn=True, mode=L.EPI_GELU_BWD, out0=o_bw, aux=aux)),
+                "f32": timeit(v2, lambda: L.gemm(A, B, M, N, K, mode=L.EPI_F32, bias=bias, out0=o_f)),
+                "rmw": timeit(v2, lambda: L.gemm(A, Bt, M, N, K, b_mn=True, mode=L.EPI_RMW_F32, out0=torch.empty_like(o_rmw).zero_())),
             }
-            outs[v2] = (o_bf, o_bfT, o_g0, o_g1, o_bw, cs, t)
+            outs[v2] = (o_bf, o_bfT, o_g0, o_g1, o_bw, o_f, o_rmw, cs, t)
         a, b = outs[False], outs[True]
         rec = {"shape": [M, N, K],
-               "equal": {n: bool(torch.equal(x, y)) for n, x, y in zip(("bf16", "bf16_T", "gelu_d", "gelu", "gelu_bwd"), a[:5], b[:5])},
-               "colsum_rel": float((a[5] - b[5]).norm() / (a[5].norm() + 1e-30)),
-               "us_v1": {k: round(v, 2) for k, v in a[6].items()}, "us_v2": {k: round(v, 2) for k, v in b[6].items()}}
+               "equal": {n: bool(torch.equal(x, y)) for n, x, y in zip(("bf16", "bf16_T", "gelu_d", "gelu", "gelu_bwd", "f32", "rmw"), a[:7], b[:7])},
+               "colsum_rel": float((a[7] - b[7]).norm() / (a[7].norm() + 1e-30)),
+               "us_v1": {k: round(v, 2) for k, v in a[8].items()}, "us_v2": {k: round(v, 2) for k, v in b[8].items()}}
         print(json.dumps(rec), flush=True)
         report.append(rec)
     os.makedirs("gpurun_out", exist_ok=True)
