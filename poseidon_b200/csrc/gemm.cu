@@ -929,6 +929,212 @@ gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
 }
 
 // =================================================================================================
+// "v3" GELU kernel (SCOT_GEMM_ASYNC_V2=2; NOT yet validated on hardware — round-2 candidate).
+//
+// Two epilogue GROUPS of four warps work on alternate tiles (group g owns accumulator buffer g and the tiles with
+// lt % 2 == g); a thread owns one accumulator row and all 64 columns of its tile. The erf-GELU arithmetic of one group
+// (17.9 instructions per element, profiles/r01_ncu_full_summary.md) then runs while the other group of the CTA — and the
+// two groups of the co-resident CTA — sit in their TMEM / staging / store waits, instead of being appended to the
+// per-tile skeleton of a single eight-warp group (37.3 us = 23.2 us skeleton + 14.1 us math in v1).
+// Per group ONE 16 KB staging tile serves both outputs in turn: gelu' is staged while it is computed and stored, the packed
+// gelu values wait in 32 registers until that store has read the tile. Producer / MMA warps as in v1.
+// =================================================================================================
+constexpr int GRP_THREADS = 128;
+template <int BMN>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_async_gelu2g_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
+  constexpr int kAccCols = 64, kTmemCols = 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = empty_bar + 8;        // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + 512);   // [2 groups][64]
+  uint8_t* tiles = smem + 1024;
+  uint8_t* out_s = tiles + (size_t)num_stages * kAStageBytes;  // [2 groups][16 KB]
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = ga.total_tiles;
+  const int tiles_per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = min(total_tiles, t_begin + tiles_per_cta);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&ga.tmA);
+    tma_prefetch_desc(&ga.tmB);
+    tma_prefetch_desc(&ga.tmOut1);
+    if (ga.has_out0) tma_prefetch_desc(&ga.tmOut0);
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], GRP_THREADS);  // only the group that owns the buffer reads it
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (as in v1) ------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int cb = t / ga.tiles_m;  // m fastest
+        const int m0 = (t - cb * ga.tiles_m) * BM, n0 = cb * ABN;
+        for (int kb = 0; kb < ga.kblocks; ++kb, ++it) {
+          const int s = it % num_stages;
+          const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
+          mbar_wait_backoff(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], kAStageBytes);
+          uint8_t* sa = tiles + (size_t)s * kAStageBytes;
+          uint8_t* sb = sa + BM * BK * 2;
+          const int k0 = kb * BK;
+          tma_load_2d(sa, &ga.tmA, &full_bar[s], k0, m0);
+          if constexpr (BMN == 0) tma_load_2d(sb, &ga.tmB, &full_bar[s], k0, n0);
+          else tma_load_2d(sb, &ga.tmB, &full_bar[s], n0, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (as in v1) ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, ABN, 0, BMN);
+      int it = 0, lt = 0;
+      for (int t = t_begin; t < t_end; ++t, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait_backoff(&tmem_empty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * kAccCols);
+        for (int i = 0; i < ga.kblocks; ++i, ++it) {
+          const int s = it % num_stages;
+          const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
+          mbar_wait_backoff(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)s * kAStageBytes);
+          const uint32_t sb = sa + BM * BK * 2;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = (BMN == 0) ? umma_smem_desc(sb + k * 32, 16, 1024)
+                                           : umma_smem_desc(sb + k * 2048, BK * 128, 1024);
+            umma_bf16(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue: two groups of four warps ------------------------------
+    const int ew = warp - 2;             // 0..7
+    const int grp = ew >> 2;             // 0: warps 2-5, 1: warps 6-9  (warp % 4 covers the four TMEM lane quarters in both)
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int gt = (ew & 3) * 32 + lane; // thread index inside the group, 0..127
+    const int row = q * 32 + lane;       // accumulator row (TMEM lane) of this thread
+    const bool issuer = (gt == 0);       // issues / tracks this group's bulk stores
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t stage_row = smem_u32(out_s) + (uint32_t)(grp * kOutTileBytes) + (uint32_t)row * 128u;
+    const uint8_t* stage_tile = out_s + grp * kOutTileBytes;
+    float* gbias = bias_s + grp * ABN;
+    // named barriers of this group: (1, 2) for group 0, (3, 4) for group 1 — immediates, so that the kernel reserves 5 ids
+#define GBAR_A()                                                                        \
+  do {                                                                                  \
+    if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(GRP_THREADS) : "memory");        \
+    else asm volatile("bar.sync 3, %0;" ::"n"(GRP_THREADS) : "memory");                 \
+  } while (0)
+#define GBAR_B()                                                                        \
+  do {                                                                                  \
+    if (grp == 0) asm volatile("bar.sync 2, %0;" ::"n"(GRP_THREADS) : "memory");        \
+    else asm volatile("bar.sync 4, %0;" ::"n"(GRP_THREADS) : "memory");                 \
+  } while (0)
+    int bias_cb = -1;
+    // this group's tiles: local index lt = grp, grp + 2, ...  (accumulator buffer lt & 1 == grp)
+    for (int lt = grp; t_begin + lt < t_end; lt += 2) {
+      const int t = t_begin + lt;
+      const int cb = t / ga.tiles_m;
+      const int m0 = (t - cb * ga.tiles_m) * BM, n0 = cb * ABN;
+      const uint32_t use = (uint32_t)(lt >> 1);  // how many times this group has used its buffer before
+      if (cb != bias_cb) {  // group-uniform
+        bias_cb = cb;
+        GBAR_A();  // previous bias no longer read
+        if (gt < ABN) gbias[gt] = (ga.bias != nullptr && n0 + gt < ga.N) ? __ldg(ga.bias + n0 + gt) : 0.f;
+        GBAR_A();
+      }
+      mbar_wait(&tmem_full_bar[grp], use & 1u);
+      tc_fence_after();
+      // the staging tile must be free before gelu' is written into it: this group's previous store (gelu of its last tile)
+      if (issuer) bulk_wait_read<0>();
+      GBAR_A();
+      uint32_t act[32];  // packed gelu of the 64 columns, staged after the gelu' store has read the tile
+#pragma unroll
+      for (int qc = 0; qc < 4; ++qc) {  // 16 accumulator columns at a time (keeps the live fp32 set small)
+        float v[16];
+        tmem_ld_32x16(tmem_base + (uint32_t)(grp * kAccCols + qc * 16) + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(gbias + qc * 16);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {  // 8 columns = one 16-byte chunk of the output row
+          const float4 ba = b4[2 * j], bb = b4[2 * j + 1];
+          const float xs[8] = {v[8 * j] + ba.x, v[8 * j + 1] + ba.y, v[8 * j + 2] + ba.z, v[8 * j + 3] + ba.w,
+                               v[8 * j + 4] + bb.x, v[8 * j + 5] + bb.y, v[8 * j + 6] + bb.z, v[8 * j + 7] + bb.w};
+          uint32_t g4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float c0, p0, c1, p1;
+            gelu_parts(xs[2 * k], c0, p0);
+            gelu_parts(xs[2 * k + 1], c1, p1);
+            g4[k] = pack_bf16x2(fmaf(xs[2 * k], p0, c0), fmaf(xs[2 * k + 1], p1, c1));  // gelu'
+            act[qc * 8 + j * 4 + k] = pack_bf16x2(xs[2 * k] * c0, xs[2 * k + 1] * c1);  // gelu
+          }
+          sts128(stage_row + ((((uint32_t)(qc * 2 + j)) ^ swz) << 4), g4[0], g4[1], g4[2], g4[3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[grp]);  // the MMA warp may refill this accumulator (tile lt + 2)
+      fence_proxy_async_smem();
+      GBAR_B();
+      if (issuer) {
+        if (ga.has_out0) {
+          tma_store_2d(&ga.tmOut0, stage_tile, n0, m0);
+          bulk_commit();
+          bulk_wait_read<0>();  // the other groups keep the SM busy meanwhile
+        }
+      }
+      GBAR_A();
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        sts128(stage_row + ((((uint32_t)c) ^ swz) << 4), act[4 * c], act[4 * c + 1], act[4 * c + 2], act[4 * c + 3]);
+      fence_proxy_async_smem();
+      GBAR_B();
+      if (issuer) {
+        tma_store_2d(&ga.tmOut1, stage_tile, n0, m0);
+        bulk_commit();
+      }
+    }
+    if (issuer) bulk_wait<0>();  // all stores of this group are performed before the grid can complete
+#undef GBAR_A
+#undef GBAR_B
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// =================================================================================================
 // SIMT reference kernel (bring-up / cross-check path; same epilogue semantics, fp32 FMA on CUDA cores)
 // =================================================================================================
 template <int MODE>
@@ -1108,10 +1314,12 @@ bool async_epi_enabled() {
 }
 
 // SCOT_GEMM_ASYNC_V2=1 selects gemm_async_epi2_kernel (round-2 candidate, see its header)
-bool async_v2_enabled() {
+// SCOT_GEMM_ASYNC_V2=2 additionally routes the GELU mode to gemm_async_gelu2g_kernel (two epilogue groups)
+int async_v2_level() {
   const char* e = getenv("SCOT_GEMM_ASYNC_V2");
-  return e != nullptr && e[0] == '1';
+  return (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
 }
+bool async_v2_enabled() { return async_v2_level() >= 1; }
 
 template <int BMN, int MODE, bool V2 = false>
 int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
@@ -1164,6 +1372,17 @@ int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N,
   void (*kern)(AsyncArgs, int);
   if constexpr (V2) kern = gemm_async_epi2_kernel<BMN, MODE>;
   else kern = gemm_async_epi_kernel<BMN, MODE>;
+  if constexpr (V2 && MODE == SCOT_EPI_GELU) {
+    // two-group variant: same shared-memory footprint (one 16 KB staging tile per group instead of one per output)
+    if (async_v2_level() >= 2) {
+      kern = gemm_async_gelu2g_kernel<BMN>;
+      static bool attr2_done = false;
+      if (!attr2_done) {
+        SCOT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 / 2));
+        attr2_done = true;
+      }
+    }
+  }
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     SCOT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 / 2));
