@@ -644,8 +644,9 @@ gemm_async_epi_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
 //   * BF16 mode: two staging tiles used alternately, `wait_group.read 1` (the previous store may still be reading);
 //   * GELU_BWD mode: no staging tile at all — the product is written in place into the aux-ring stage that delivered the
 //     saved gelu' tile (same 128 x 64 bf16 128B-swizzled layout) and stored from there; the stage goes back to the
-//     producer when that store has read it (aux_empty: one arrival by the issuer instead of 256 by the readers). This
-//     frees 16 KB: three operand stages instead of two;
+//     producer when that store has read it (aux_empty: one arrival by the issuer, at the start of the next tile, instead
+//     of 256 by the readers). This frees 16 KB: three operand stages instead of two (K = 384 / 768 dgrads have 6 / 12
+//     k-blocks per tile, two stages starve the MMA: 31 % of the v1 samples wait on the aux / accumulator barriers);
 //   * GELU mode: bias kept in shared memory (one broadcast LDS.128 per four columns) instead of 32 registers per thread,
 //     so that both packed outputs (32 registers) fit next to the accumulator row without spilling at 2 CTAs / SM.
 // =================================================================================================
@@ -792,6 +793,15 @@ gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[buf]);  // the MMA warp may start the tile after next in this accumulator
+      if constexpr (MODE == SCOT_EPI_GELU_BWD) {
+        // hand the OTHER aux stage back to the producer as early as possible (it must be re-loaded for tile lt + 1 while
+        // this tile is processed): its in-place result was stored at the end of the previous tile; only the issuer's warp
+        // waits here for that store to have read the stage, the other seven warps go on with the arithmetic
+        if (issuer && lt > 0) {
+          bulk_wait_read<0>();
+          mbar_arrive(&aux_empty_bar[buf ^ 1]);
+        }
+      }
       // ---- arithmetic first: results as packed bf16 in registers ----
       uint32_t o0[16];
       uint32_t o1[(MODE == SCOT_EPI_GELU) ? 16 : 1];
@@ -889,12 +899,6 @@ gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
         } else {
           tma_store_2d(&ga.tmOut0, aux_s + buf * kOutTileBytes, n0, m0);
           bulk_commit();
-          // the store issued for the PREVIOUS tile (other aux stage) has read its source by now or we wait for it: hand
-          // that stage back to the producer
-          if (lt > 0) {
-            bulk_wait_read<1>();
-            mbar_arrive(&aux_empty_bar[buf ^ 1]);
-          }
         }
       }
       if constexpr (MODE == SCOT_EPI_GELU_BWD) {
