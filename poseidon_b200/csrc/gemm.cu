@@ -650,6 +650,177 @@ gemm_async_epi_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
 //   * GELU mode: bias kept in shared memory (one broadcast LDS.128 per four columns) instead of 32 registers per thread,
 //     so that both packed outputs (32 registers) fit next to the accumulator row without spilling at 2 CTAs / SM.
 // =================================================================================================
+// Epilogue of the v2 kernels (eight warps, one thread per accumulator row and 32-column half), shared by
+// gemm_async_epi2_kernel and gemm_async_smallk_kernel.
+template <int MODE>
+__device__ __forceinline__ void async_epilogue_v2(const AsyncArgs& ga, int warp, int lane, int t_begin, int t_end,
+                                                  uint32_t tmem_base, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar,
+                                                  uint64_t* aux_full_bar, uint64_t* aux_empty_bar, float* bias_s,
+                                                  uint8_t* aux_s, uint8_t* out_s) {
+  constexpr int kAccCols = 64;
+  // ------------------------------ epilogue (8 warps) ------------------------------
+  const int ew = warp - 2;             // 0..7
+  const int q = warp & 3;              // TMEM lane quarter this warp may access
+  const int half = ew >> 2;            // which 32-column half of the tile this warp converts
+  const int et = ew * 32 + lane;       // 0..255
+  const int row = q * 32 + lane;       // accumulator row (TMEM lane) of this thread
+  const bool issuer = (et == 0);       // issues / tracks the bulk stores
+  const uint32_t swz = (uint32_t)(row & 7);
+  const uint32_t row_off = (uint32_t)row * 128u;
+  float cs0 = 0.f, cs1 = 0.f;          // GELU_BWD: running sums of columns 2*(et&31), +1 over rows (et>>5)*16..+15
+  int bias_cb = -1;
+  int lt = 0;
+  for (int t = t_begin; t < t_end; ++t, ++lt) {
+    const int cb = t / ga.tiles_m;
+    const int m0 = (t - cb * ga.tiles_m) * BM, n0 = cb * ABN;
+    const int buf = lt & 1;
+    if constexpr (MODE != SCOT_EPI_GELU_BWD && MODE != SCOT_EPI_RMW_F32) {
+      if (cb != bias_cb) {  // block-uniform: every epilogue thread sees the same tile sequence
+        bias_cb = cb;
+        asm volatile("bar.sync 3, %0;" ::"n"(EPI_THREADS) : "memory");  // readers of the previous column block's bias are done
+        if (et < ABN) bias_s[et] = (ga.bias != nullptr && n0 + et < ga.N) ? __ldg(ga.bias + n0 + et) : 0.f;
+        asm volatile("bar.sync 3, %0;" ::"n"(EPI_THREADS) : "memory");
+      }
+    }
+    mbar_wait(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
+    tc_fence_after();
+    float v[32];
+    tmem_ld_32x32(tmem_base + (uint32_t)(buf * kAccCols + half * 32) + ((uint32_t)(q * 32) << 16), v);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(&tmem_empty_bar[buf]);  // the MMA warp may start the tile after next in this accumulator
+    if constexpr (MODE == SCOT_EPI_GELU_BWD) {
+      // hand the OTHER aux stage back to the producer as early as possible (it must be re-loaded for tile lt + 1 while
+      // this tile is processed): its in-place result was stored at the end of the previous tile; only the issuer's warp
+      // waits here for that store to have read the stage, the other seven warps go on with the arithmetic
+      if (issuer && lt > 0) {
+        bulk_wait_read<0>();
+        mbar_arrive(&aux_empty_bar[buf ^ 1]);
+      }
+    }
+    // ---- arithmetic first: results as packed bf16 in registers ----
+    uint32_t o0[16];
+    uint32_t o1[(MODE == SCOT_EPI_GELU) ? 16 : 1];
+    uint32_t stage_base;  // shared-memory address of this thread's row in the tile that will be stored
+    if constexpr (MODE == SCOT_EPI_GELU) {
+      const float4* b4 = reinterpret_cast<const float4*>(bias_s + half * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = b4[j];
+        const float xs[4] = {v[4 * j] + bb.x, v[4 * j + 1] + bb.y, v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w};
+        float c[4], p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gelu_parts(xs[k], c[k], p[k]);
+        o0[2 * j] = pack_bf16x2(fmaf(xs[0], p[0], c[0]), fmaf(xs[1], p[1], c[1]));      // gelu'
+        o0[2 * j + 1] = pack_bf16x2(fmaf(xs[2], p[2], c[2]), fmaf(xs[3], p[3], c[3]));
+        o1[2 * j] = pack_bf16x2(xs[0] * c[0], xs[1] * c[1]);                             // gelu
+        o1[2 * j + 1] = pack_bf16x2(xs[2] * c[2], xs[3] * c[3]);
+      }
+      stage_base = smem_u32(out_s) + row_off;
+    } else if constexpr (MODE == SCOT_EPI_BF16) {
+      const float4* b4 = reinterpret_cast<const float4*>(bias_s + half * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = b4[j];
+        o0[2 * j] = pack_bf16x2(v[4 * j] + bb.x, v[4 * j + 1] + bb.y);
+        o0[2 * j + 1] = pack_bf16x2(v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+      }
+      stage_base = smem_u32(out_s) + (uint32_t)(buf * kOutTileBytes) + row_off;
+    } else if constexpr (MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32) {
+      // fp32 output: this thread's 32 columns are one 128-byte row of its half's 128 x 32 fp32 box (128B swizzle)
+      if constexpr (MODE == SCOT_EPI_F32) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = b4[j];
+          v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+        }
+      }
+      stage_base = smem_u32(out_s) + (uint32_t)(half * kOutTileBytes) + row_off;
+    } else {  // GELU_BWD: dh = acc * gelu'(h); gelu'(h) sits in aux stage `buf`, the product replaces it in place
+      mbar_wait(&aux_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
+      stage_base = smem_u32(aux_s) + (uint32_t)(buf * kOutTileBytes) + row_off;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 a = lds128(stage_base + ((((uint32_t)(half * 4 + j)) ^ swz) << 4));
+        const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 g = unpack_bf16x2(w[k]);
+          o0[4 * j + k] = pack_bf16x2(v[j * 8 + 2 * k] * g.x, v[j * 8 + 2 * k + 1] * g.y);
+        }
+      }
+    }
+    // ---- now the tile that receives the results must be free ----
+    if constexpr (MODE == SCOT_EPI_BF16) {
+      if (issuer) bulk_wait_read<1>();   // the store issued two tiles ago used this buffer; the last one may still read
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+    } else if constexpr (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32) {
+      if (issuer) bulk_wait_read<0>();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+    }
+    // GELU_BWD: every thread rewrites exactly the 64 bytes it has just read; no other thread touches them before bar.sync 2
+    if constexpr (MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)  // eight 16-byte chunks = the whole 128-byte row of this half
+        sts128(stage_base + ((((uint32_t)j) ^ swz) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+               __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = (((uint32_t)(half * 4 + j)) ^ swz) << 4;
+        sts128(stage_base + off, o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
+        if constexpr (MODE == SCOT_EPI_GELU)
+          sts128(stage_base + kOutTileBytes + off, o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+    if (issuer) {
+      if constexpr (MODE == SCOT_EPI_GELU) {
+        if (ga.has_out0) tma_store_2d(&ga.tmOut0, out_s, n0, m0);
+        tma_store_2d(&ga.tmOut1, out_s + kOutTileBytes, n0, m0);
+        bulk_commit();
+      } else if constexpr (MODE == SCOT_EPI_BF16) {
+        tma_store_2d(&ga.tmOut0, out_s + buf * kOutTileBytes, n0, m0);
+        bulk_commit();
+      } else if constexpr (MODE == SCOT_EPI_F32) {
+        tma_store_2d(&ga.tmOut0, out_s, n0, m0);  // fp32 tensor map, box {32, 128}: one store per column half
+        if (n0 + 32 < ga.N) tma_store_2d(&ga.tmOut0, out_s + kOutTileBytes, n0 + 32, m0);
+        bulk_commit();
+      } else if constexpr (MODE == SCOT_EPI_RMW_F32) {
+        tma_reduce_add_2d(&ga.tmOut0, out_s, n0, m0);  // out += tile, the fp32 add is performed by the L2
+        if (n0 + 32 < ga.N) tma_reduce_add_2d(&ga.tmOut0, out_s + kOutTileBytes, n0 + 32, m0);
+        bulk_commit();
+      } else {
+        tma_store_2d(&ga.tmOut0, aux_s + buf * kOutTileBytes, n0, m0);
+        bulk_commit();
+      }
+    }
+    if constexpr (MODE == SCOT_EPI_GELU_BWD) {
+      // bias gradient: column sums of the bf16 values just staged (rows >= M hold zeros: their A rows were zero-filled)
+      const int cp = et & 31, rg = et >> 5;
+      const uint32_t chunk = (uint32_t)(cp >> 2), word = (uint32_t)(cp & 3) * 4;
+      const uint32_t obase = smem_u32(aux_s) + (uint32_t)(buf * kOutTileBytes) + word;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        const int r = rg * 16 + rr;
+        const float2 f = unpack_bf16x2(lds32(obase + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+        cs0 += f.x;
+        cs1 += f.y;
+      }
+      const bool last_of_col = (t + 1 >= t_end) || ((t + 1) / ga.tiles_m != cb);
+      if (last_of_col && ga.colsum != nullptr) {
+        const int c = n0 + 2 * cp;
+        if (c < ga.N) atomicAdd(ga.colsum + c, cs0);
+        if (c + 1 < ga.N) atomicAdd(ga.colsum + c + 1, cs1);
+        cs0 = cs1 = 0.f;
+      }
+    }
+  }
+  if (issuer) bulk_wait<0>();  // all stores of this CTA are performed before the grid can complete
+}
+
 template <int BMN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
@@ -762,167 +933,8 @@ gemm_async_epi2_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
       }
     }
   } else {
-    // ------------------------------ epilogue (8 warps) ------------------------------
-    const int ew = warp - 2;             // 0..7
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = ew >> 2;            // which 32-column half of the tile this warp converts
-    const int et = ew * 32 + lane;       // 0..255
-    const int row = q * 32 + lane;       // accumulator row (TMEM lane) of this thread
-    const bool issuer = (et == 0);       // issues / tracks the bulk stores
-    const uint32_t swz = (uint32_t)(row & 7);
-    const uint32_t row_off = (uint32_t)row * 128u;
-    float cs0 = 0.f, cs1 = 0.f;          // GELU_BWD: running sums of columns 2*(et&31), +1 over rows (et>>5)*16..+15
-    int bias_cb = -1;
-    int lt = 0;
-    for (int t = t_begin; t < t_end; ++t, ++lt) {
-      const int cb = t / ga.tiles_m;
-      const int m0 = (t - cb * ga.tiles_m) * BM, n0 = cb * ABN;
-      const int buf = lt & 1;
-      if constexpr (MODE != SCOT_EPI_GELU_BWD && MODE != SCOT_EPI_RMW_F32) {
-        if (cb != bias_cb) {  // block-uniform: every epilogue thread sees the same tile sequence
-          bias_cb = cb;
-          asm volatile("bar.sync 3, %0;" ::"n"(EPI_THREADS) : "memory");  // readers of the previous column block's bias are done
-          if (et < ABN) bias_s[et] = (ga.bias != nullptr && n0 + et < ga.N) ? __ldg(ga.bias + n0 + et) : 0.f;
-          asm volatile("bar.sync 3, %0;" ::"n"(EPI_THREADS) : "memory");
-        }
-      }
-      mbar_wait(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
-      tc_fence_after();
-      float v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t)(buf * kAccCols + half * 32) + ((uint32_t)(q * 32) << 16), v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[buf]);  // the MMA warp may start the tile after next in this accumulator
-      if constexpr (MODE == SCOT_EPI_GELU_BWD) {
-        // hand the OTHER aux stage back to the producer as early as possible (it must be re-loaded for tile lt + 1 while
-        // this tile is processed): its in-place result was stored at the end of the previous tile; only the issuer's warp
-        // waits here for that store to have read the stage, the other seven warps go on with the arithmetic
-        if (issuer && lt > 0) {
-          bulk_wait_read<0>();
-          mbar_arrive(&aux_empty_bar[buf ^ 1]);
-        }
-      }
-      // ---- arithmetic first: results as packed bf16 in registers ----
-      uint32_t o0[16];
-      uint32_t o1[(MODE == SCOT_EPI_GELU) ? 16 : 1];
-      uint32_t stage_base;  // shared-memory address of this thread's row in the tile that will be stored
-      if constexpr (MODE == SCOT_EPI_GELU) {
-        const float4* b4 = reinterpret_cast<const float4*>(bias_s + half * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = b4[j];
-          const float xs[4] = {v[4 * j] + bb.x, v[4 * j + 1] + bb.y, v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w};
-          float c[4], p[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) gelu_parts(xs[k], c[k], p[k]);
-          o0[2 * j] = pack_bf16x2(fmaf(xs[0], p[0], c[0]), fmaf(xs[1], p[1], c[1]));      // gelu'
-          o0[2 * j + 1] = pack_bf16x2(fmaf(xs[2], p[2], c[2]), fmaf(xs[3], p[3], c[3]));
-          o1[2 * j] = pack_bf16x2(xs[0] * c[0], xs[1] * c[1]);                             // gelu
-          o1[2 * j + 1] = pack_bf16x2(xs[2] * c[2], xs[3] * c[3]);
-        }
-        stage_base = smem_u32(out_s) + row_off;
-      } else if constexpr (MODE == SCOT_EPI_BF16) {
-        const float4* b4 = reinterpret_cast<const float4*>(bias_s + half * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = b4[j];
-          o0[2 * j] = pack_bf16x2(v[4 * j] + bb.x, v[4 * j + 1] + bb.y);
-          o0[2 * j + 1] = pack_bf16x2(v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
-        }
-        stage_base = smem_u32(out_s) + (uint32_t)(buf * kOutTileBytes) + row_off;
-      } else if constexpr (MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32) {
-        // fp32 output: this thread's 32 columns are one 128-byte row of its half's 128 x 32 fp32 box (128B swizzle)
-        if constexpr (MODE == SCOT_EPI_F32) {
-          const float4* b4 = reinterpret_cast<const float4*>(bias_s + half * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = b4[j];
-            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-          }
-        }
-        stage_base = smem_u32(out_s) + (uint32_t)(half * kOutTileBytes) + row_off;
-      } else {  // GELU_BWD: dh = acc * gelu'(h); gelu'(h) sits in aux stage `buf`, the product replaces it in place
-        mbar_wait(&aux_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
-        stage_base = smem_u32(aux_s) + (uint32_t)(buf * kOutTileBytes) + row_off;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 a = lds128(stage_base + ((((uint32_t)(half * 4 + j)) ^ swz) << 4));
-          const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 g = unpack_bf16x2(w[k]);
-            o0[4 * j + k] = pack_bf16x2(v[j * 8 + 2 * k] * g.x, v[j * 8 + 2 * k + 1] * g.y);
-          }
-        }
-      }
-      // ---- now the tile that receives the results must be free ----
-      if constexpr (MODE == SCOT_EPI_BF16) {
-        if (issuer) bulk_wait_read<1>();   // the store issued two tiles ago used this buffer; the last one may still read
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-      } else if constexpr (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32) {
-        if (issuer) bulk_wait_read<0>();
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-      }
-      // GELU_BWD: every thread rewrites exactly the 64 bytes it has just read; no other thread touches them before bar.sync 2
-      if constexpr (MODE == SCOT_EPI_F32 || MODE == SCOT_EPI_RMW_F32) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)  // eight 16-byte chunks = the whole 128-byte row of this half
-          sts128(stage_base + ((((uint32_t)j) ^ swz) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                 __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t off = (((uint32_t)(half * 4 + j)) ^ swz) << 4;
-          sts128(stage_base + off, o0[4 * j], o0[4 * j + 1], o0[4 * j + 2], o0[4 * j + 3]);
-          if constexpr (MODE == SCOT_EPI_GELU)
-            sts128(stage_base + kOutTileBytes + off, o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
-        }
-      }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
-      if (issuer) {
-        if constexpr (MODE == SCOT_EPI_GELU) {
-          if (ga.has_out0) tma_store_2d(&ga.tmOut0, out_s, n0, m0);
-          tma_store_2d(&ga.tmOut1, out_s + kOutTileBytes, n0, m0);
-          bulk_commit();
-        } else if constexpr (MODE == SCOT_EPI_BF16) {
-          tma_store_2d(&ga.tmOut0, out_s + buf * kOutTileBytes, n0, m0);
-          bulk_commit();
-        } else if constexpr (MODE == SCOT_EPI_F32) {
-          tma_store_2d(&ga.tmOut0, out_s, n0, m0);  // fp32 tensor map, box {32, 128}: one store per column half
-          if (n0 + 32 < ga.N) tma_store_2d(&ga.tmOut0, out_s + kOutTileBytes, n0 + 32, m0);
-          bulk_commit();
-        } else if constexpr (MODE == SCOT_EPI_RMW_F32) {
-          tma_reduce_add_2d(&ga.tmOut0, out_s, n0, m0);  // out += tile, the fp32 add is performed by the L2
-          if (n0 + 32 < ga.N) tma_reduce_add_2d(&ga.tmOut0, out_s + kOutTileBytes, n0 + 32, m0);
-          bulk_commit();
-        } else {
-          tma_store_2d(&ga.tmOut0, aux_s + buf * kOutTileBytes, n0, m0);
-          bulk_commit();
-        }
-      }
-      if constexpr (MODE == SCOT_EPI_GELU_BWD) {
-        // bias gradient: column sums of the bf16 values just staged (rows >= M hold zeros: their A rows were zero-filled)
-        const int cp = et & 31, rg = et >> 5;
-        const uint32_t chunk = (uint32_t)(cp >> 2), word = (uint32_t)(cp & 3) * 4;
-        const uint32_t obase = smem_u32(aux_s) + (uint32_t)(buf * kOutTileBytes) + word;
-#pragma unroll
-        for (int rr = 0; rr < 16; ++rr) {
-          const int r = rg * 16 + rr;
-          const float2 f = unpack_bf16x2(lds32(obase + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
-          cs0 += f.x;
-          cs1 += f.y;
-        }
-        const bool last_of_col = (t + 1 >= t_end) || ((t + 1) / ga.tiles_m != cb);
-        if (last_of_col && ga.colsum != nullptr) {
-          const int c = n0 + 2 * cp;
-          if (c < ga.N) atomicAdd(ga.colsum + c, cs0);
-          if (c + 1 < ga.N) atomicAdd(ga.colsum + c + 1, cs1);
-          cs0 = cs1 = 0.f;
-        }
-      }
-    }
-    if (issuer) bulk_wait<0>();  // all stores of this CTA are performed before the grid can complete
+    async_epilogue_v2<MODE>(ga, warp, lane, t_begin, t_end, tmem_base, tmem_full_bar, tmem_empty_bar, aux_full_bar,
+                            aux_empty_bar, bias_s, aux_s, out_s);
   }
   tc_fence_before();
   __syncthreads();
@@ -1139,6 +1151,194 @@ gemm_async_gelu2g_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
 }
 
 // =================================================================================================
+// Small-K kernel (SCOT_GEMM_ASYNC_V2 bit 2 (=4); NOT yet validated on hardware — round-2 candidate), K <= 128.
+//
+// The stage-0 GEMMs have K = 96: per 128 x 64 tile the v1 / v2 producer moves 48 KB through the TMA unit, of which 16 KB
+// are the SAME 64 x 96 weight tile for every row tile of a column block and 12 KB are out-of-bounds zero fill of the
+// second, half-empty 64-wide k-block. Here (a) the weight tile of a column block is loaded ONCE into a resident
+// shared-memory region (b_full / b_empty barriers; a CTA walks down one column block, so it reloads at most twice) and
+// (b) a K tail of 32 elements uses its own 32-wide boxes (64-byte swizzle atom, UMMA SWIZZLE_64B descriptors) instead of
+// a zero-filled 64-wide block: 24 KB of operand traffic per tile instead of 48 KB. The A ring holds one k-block per
+// 16 KB stage. Epilogue = async_epilogue_v2.
+// =================================================================================================
+struct AsyncArgsS {
+  AsyncArgs a;
+  CUtensorMap tmA_tail, tmB_tail;
+  int tail_k;  // 0: every k-block is full; 32: the last k-block has 32 elements
+};
+constexpr int kSmallAStage = BM * BK * 2;        // 16 KB
+constexpr int kSmallBBlock = ABN * BK * 2;       // 8 KB per resident B k-block
+constexpr int kSmallBBytes = 2 * kSmallBBlock;   // up to two k-blocks (K <= 128)
+
+// K-major operand tile with 64-byte rows (32 bf16 along K), 64-byte swizzle: 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t umma_smem_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((16u >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((512u >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+  return d;
+}
+
+template <int BMN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_async_smallk_kernel(const __grid_constant__ AsyncArgsS gs, int num_stages) {
+  constexpr bool kHasAux = (MODE == SCOT_EPI_GELU_BWD);
+  constexpr int kAccCols = 64, kTmemCols = 128;
+  const AsyncArgs& ga = gs.a;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = empty_bar + 8;        // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint64_t* aux_full_bar = tmem_empty_bar + 2;    // [2]
+  uint64_t* aux_empty_bar = aux_full_bar + 2;     // [2]
+  uint64_t* b_full_bar = aux_empty_bar + 2;       // [1]
+  uint64_t* b_empty_bar = b_full_bar + 1;         // [1]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(b_empty_bar + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + 512);
+  uint8_t* b_s = smem + 1024;                                              // resident weight tile, [2][8 KB]
+  uint8_t* a_ring = b_s + kSmallBBytes;                                    // [num_stages][16 KB]
+  uint8_t* aux_s = a_ring + (size_t)num_stages * kSmallAStage;             // [2][16 KB] (GELU_BWD only; doubles as staging)
+  uint8_t* out_s = aux_s + (kHasAux ? 2 * kOutTileBytes : 0);
+
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = ga.total_tiles;
+  const int tiles_per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = min(total_tiles, t_begin + tiles_per_cta);
+  const int kb_n = ga.kblocks;           // 1 or 2
+  const int tail = gs.tail_k;            // 0 or 32
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&ga.tmA);
+    tma_prefetch_desc(&ga.tmB);
+    tma_prefetch_desc(&ga.tmOut0);
+    if (tail) {
+      tma_prefetch_desc(&gs.tmA_tail);
+      tma_prefetch_desc(&gs.tmB_tail);
+    }
+    if (kHasAux) tma_prefetch_desc(&ga.tmAux);
+    if (MODE == SCOT_EPI_GELU) tma_prefetch_desc(&ga.tmOut1);
+    for (int s = 0; s < num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], EPI_THREADS);
+      mbar_init(&aux_full_bar[b], 1);
+      mbar_init(&aux_empty_bar[b], 1);
+    }
+    mbar_init(b_full_bar, 1);
+    mbar_init(b_empty_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int it = 0, lt = 0, cur_cb = -1;
+      uint32_t b_use = 0;
+      const uint32_t b_bytes = (uint32_t)((kb_n - (tail ? 1 : 0)) * kSmallBBlock + (tail ? ABN * tail * 2 : 0));
+      for (int t = t_begin; t < t_end; ++t, ++lt) {
+        const int cb = t / ga.tiles_m;  // m fastest
+        const int m0 = (t - cb * ga.tiles_m) * BM, n0 = cb * ABN;
+        if (cb != cur_cb) {
+          // every MMA that read the previous weight tile has completed (committed by the MMA warp after the last tile of
+          // the previous column block); the first use passes immediately
+          mbar_wait_backoff(b_empty_bar, (b_use & 1u) ^ 1u);
+          mbar_expect_tx(b_full_bar, b_bytes);
+          for (int kb = 0; kb < kb_n; ++kb) {
+            const bool is_tail = tail && kb == kb_n - 1;
+            const CUtensorMap* tm = is_tail ? &gs.tmB_tail : &ga.tmB;
+            if constexpr (BMN == 0) tma_load_2d(b_s + kb * kSmallBBlock, tm, b_full_bar, kb * BK, n0);
+            else tma_load_2d(b_s + kb * kSmallBBlock, tm, b_full_bar, n0, kb * BK);
+          }
+          cur_cb = cb;
+          ++b_use;
+        }
+        if constexpr (kHasAux) {
+          const int as = lt & 1;
+          mbar_wait_backoff(&aux_empty_bar[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&aux_full_bar[as], kOutTileBytes);
+          tma_load_2d(aux_s + as * kOutTileBytes, &ga.tmAux, &aux_full_bar[as], n0, m0);
+        }
+        for (int kb = 0; kb < kb_n; ++kb, ++it) {
+          const int s = it % num_stages;
+          const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
+          const bool is_tail = tail && kb == kb_n - 1;
+          mbar_wait_backoff(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], is_tail ? (uint32_t)(BM * tail * 2) : (uint32_t)kSmallAStage);
+          tma_load_2d(a_ring + (size_t)s * kSmallAStage, is_tail ? &gs.tmA_tail : &ga.tmA, &full_bar[s], kb * BK, m0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, ABN, 0, BMN);
+      int it = 0, lt = 0, cur_cb = -1;
+      uint32_t b_use = 0;
+      for (int t = t_begin; t < t_end; ++t, ++lt) {
+        const int cb = t / ga.tiles_m;
+        if (cb != cur_cb) {
+          mbar_wait_backoff(b_full_bar, b_use & 1u);  // the weight tile of this column block has landed
+          cur_cb = cb;
+          ++b_use;
+        }
+        const int buf = lt & 1;
+        mbar_wait_backoff(&tmem_empty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * kAccCols);
+        for (int i = 0; i < kb_n; ++i, ++it) {
+          const int s = it % num_stages;
+          const uint32_t ph = (uint32_t)(it / num_stages) & 1u;
+          const bool is_tail = tail && i == kb_n - 1;
+          mbar_wait_backoff(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(a_ring + (size_t)s * kSmallAStage);
+          const uint32_t sb = smem_u32(b_s + i * kSmallBBlock);
+          const int nk = is_tail ? tail / UMMA_K : BK / UMMA_K;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            if (k < nk) {
+              const uint64_t da = is_tail ? umma_smem_desc_sw64(sa + k * 32) : umma_smem_desc(sa + k * 32, 16, 1024);
+              const uint64_t db = (BMN == 0) ? (is_tail ? umma_smem_desc_sw64(sb + k * 32) : umma_smem_desc(sb + k * 32, 16, 1024))
+                                             : umma_smem_desc(sb + k * 2048, BK * 128, 1024);
+              umma_bf16(tacc, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[buf]);
+        const bool last_of_cb = (t + 1 >= t_end) || ((t + 1) / ga.tiles_m != cb);
+        if (last_of_cb) umma_commit(b_empty_bar);  // arrives once every MMA issued so far has read its operands
+      }
+    }
+  } else {
+    async_epilogue_v2<MODE>(ga, warp, lane, t_begin, t_end, tmem_base, tmem_full_bar, tmem_empty_bar, aux_full_bar,
+                            aux_empty_bar, bias_s, aux_s, out_s);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// =================================================================================================
 // SIMT reference kernel (bring-up / cross-check path; same epilogue semantics, fp32 FMA on CUDA cores)
 // =================================================================================================
 template <int MODE>
@@ -1192,13 +1392,13 @@ int get_encode_fn() {
 
 // inner = contiguous dimension (elements), outer = strided dimension, ld = stride of outer in elements
 int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-              uint32_t box_outer) {
+              uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SCOT_REQUIRE(r == CUDA_SUCCESS,
                "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, ptr,
@@ -1318,12 +1518,14 @@ bool async_epi_enabled() {
 }
 
 // SCOT_GEMM_ASYNC_V2=1 selects gemm_async_epi2_kernel (round-2 candidate, see its header)
-// SCOT_GEMM_ASYNC_V2=2 additionally routes the GELU mode to gemm_async_gelu2g_kernel (two epilogue groups)
+// SCOT_GEMM_ASYNC_V2 is a bit mask: 1 = v2 kernels, 2 = + two-group GELU kernel (gemm_async_gelu2g_kernel), 4 = + small-K
+// kernel with the resident weight tile (gemm_async_smallk_kernel, K <= 128). 0 / unset = the validated v1 kernels.
 int async_v2_level() {
   const char* e = getenv("SCOT_GEMM_ASYNC_V2");
-  return (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+  const int v = e != nullptr ? atoi(e) : 0;
+  return (v >= 1 && v <= 7) ? (v | 1) : 0;
 }
-bool async_v2_enabled() { return async_v2_level() >= 1; }
+bool async_v2_enabled() { return async_v2_level() != 0; }
 
 template <int BMN, int MODE, bool V2 = false>
 int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
@@ -1364,6 +1566,44 @@ int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N,
   ga.bias = ep.bias;
   ga.colsum = ep.colsum;
   ga.has_out0 = ep.out0 != nullptr;
+  if constexpr (V2) {
+    // small K: resident weight tile + exact K tail (see gemm_async_smallk_kernel)
+    const int tail_k = K % BK;
+    if ((async_v2_level() & 4) && K <= 2 * BK && (tail_k == 0 || tail_k == 32) &&
+        !(MODE == SCOT_EPI_GELU && (async_v2_level() & 2))) {
+      AsyncArgsS gs;
+      memset(&gs, 0, sizeof(gs));
+      gs.a = ga;
+      gs.tail_k = tail_k;
+      if (tail_k) {
+        const int k0 = K - tail_k;  // the tail boxes are addressed with the same (k, row) coordinates as the full ones
+        (void)k0;
+        rc = make_tmap(&gs.tmA_tail, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 32, BM, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        if (BMN == 0) rc = make_tmap(&gs.tmB_tail, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 32, ABN, CU_TENSOR_MAP_SWIZZLE_64B);
+        else rc = make_tmap(&gs.tmB_tail, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 32);
+        if (rc) return rc;
+      }
+      const size_t staging_s = (MODE == SCOT_EPI_GELU_BWD ? 0 : 2) * (size_t)kOutTileBytes;
+      const size_t fixed_s = 1024 + 1024 + kSmallBBytes + (MODE == SCOT_EPI_GELU_BWD ? 2 * kOutTileBytes : 0) + staging_s;
+      const size_t budget_s = (size_t)(227 * 1024) / 2 - 1024;
+      int stages_s = (int)((budget_s - fixed_s) / kSmallAStage);
+      if (stages_s > 6) stages_s = 6;
+      SCOT_REQUIRE(stages_s >= 2, "gemm(small K): shared memory budget");
+      const size_t smem_s = fixed_s + (size_t)stages_s * kSmallAStage;
+      auto kern_s = gemm_async_smallk_kernel<BMN, MODE>;
+      static bool attr_s_done = false;
+      if (!attr_s_done) {
+        SCOT_CHECK_CUDA(cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 / 2));
+        attr_s_done = true;
+      }
+      const int max_ctas_s = g_num_sms * 2;
+      const int grid_s = ga.total_tiles < max_ctas_s ? ga.total_tiles : max_ctas_s;
+      SCOT_CHECK_CUDA(scot_launch_pdl(kern_s, dim3(grid_s), dim3(GEMM_THREADS), smem_s, stream, gs, stages_s));
+      SCOT_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   // staging tiles: v1 one per output (+ the aux ring for GELU_BWD); v2: two for BF16, the aux ring alone for GELU_BWD
   const size_t staging = V2 ? (MODE == SCOT_EPI_GELU_BWD ? 0 : 2) * (size_t)kOutTileBytes  // GELU: two outputs; BF16: two
                             : (MODE == SCOT_EPI_GELU ? 2 : 1) * (size_t)kOutTileBytes;          // buffers; fp32: two halves
@@ -1378,7 +1618,7 @@ int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N,
   else kern = gemm_async_epi_kernel<BMN, MODE>;
   if constexpr (V2 && MODE == SCOT_EPI_GELU) {
     // two-group variant: same shared-memory footprint (one 16 KB staging tile per group instead of one per output)
-    if (async_v2_level() >= 2) {
+    if (async_v2_level() & 2) {
       kern = gemm_async_gelu2g_kernel<BMN>;
       static bool attr2_done = false;
       if (!attr2_done) {
