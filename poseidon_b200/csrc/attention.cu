@@ -496,6 +496,38 @@ __device__ __forceinline__ void fold_bias_to_table(const float* __restrict__ sac
   }
 }
 
+// Same fold for 16 x 16 windows with the address arithmetic taken out of the inner loop (ATTN_DQ_FOLD2 candidate, not yet
+// run on hardware): a slot address splits into f(m) + g(n) with n = m - (16 dp + dq), and stepping one window row down
+// (m += 16, n += 16) adds the constant 16 N + 256. Per (query, key) pair the loop below is one LDS, one FADD and one
+// pointer add instead of ~20 integer instructions — the fold is 14 % of the dq kernel's executed instructions
+// (profiles/r01_ncu_full_summary.md). Summation order differs from fold_bias_to_table (fp32 reassociation only).
+template <int NWARP>
+__device__ __forceinline__ void fold_bias_to_table16(const float* __restrict__ sacc, float* __restrict__ dtab, int h, int heads,
+                                                     int rg, int tid, int nthreads) {
+  constexpr int WS = 16, N = 256, MT = 16, SIDE = 31, TABN = SIDE * SIDE, ACC = 16 * N;
+  static_assert(MT >= NWARP, "one window per iteration");
+  const int mt_lo = (MT > NWARP) ? rg * NWARP : 0;
+  const int mt_hi = (MT > NWARP) ? mt_lo + NWARP : MT;
+  for (int r = tid; r < TABN; r += nthreads) {
+    const int dp = r / SIDE - (WS - 1), dq = r % SIDE - (WS - 1);
+    int pm0 = dp > 0 ? dp : 0, pm1 = dp < 0 ? WS + dp : WS;
+    const int qm0 = dq > 0 ? dq : 0, qm1 = dq < 0 ? WS + dq : WS;
+    pm0 = pm0 > mt_lo ? pm0 : mt_lo;
+    pm1 = pm1 < mt_hi ? pm1 : mt_hi;
+    if (pm1 <= pm0) continue;
+    const int d = dp * WS + dq;
+    float acc = 0.f;
+    for (int qm = qm0; qm < qm1; ++qm) {
+      const int m = pm0 * WS + qm, n = m - d;
+      const float* p = sacc + ((m >> 4) - mt_lo) * ACC + ((m >> 3) & 1) * 64 + (m & 7) * 4 + (n >> 3) * 128 + (n & 1) * 32 +
+                       ((n & 7) >> 1);
+#pragma unroll 4
+      for (int pm = pm0; pm < pm1; ++pm, p += ACC + 256) acc += *p;
+    }
+    atomicAdd(dtab + r * heads + h, acc);
+  }
+}
+
 // =================================================================================================
 // backward, kernel 1: dq (+ relative-position-bias and logit-scale gradients)
 //   CTA = (head, row group, window chunk); every warp owns one 16-query tile and loops over windows;
@@ -518,7 +550,9 @@ struct DqCfg {
                                  + (size_t)TABN * 4 + (size_t)NWARP * 16 * 4 /*inv norms*/;
 };
 
-template <int WS, int HD, int NWARP, bool SHIFT>
+// FOLD2 (SCOT_ATTN_DQ_FOLD2=1, 16 x 16 windows only): bias-gradient fold with fold_bias_to_table16 — candidate, never run on
+// hardware; the default instantiations (FOLD2 = false) compile to the same SASS as before the parameter existed.
+template <int WS, int HD, int NWARP, bool SHIFT, bool FOLD2 = false>
 __global__ void __launch_bounds__(NWARP * 32)
 attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf, const bf16* __restrict__ do_buf,
                    const float* __restrict__ lse, const float* __restrict__ tab2, const float* __restrict__ alpha,
@@ -699,7 +733,8 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
   // fold this CTA's bias-gradient accumulators (fragment order, summed over its windows) onto the (2ws-1)^2 table of
   // the head through the relative position index (HF:512-523) and add the <= 961 table entries to the layer's
   // gradient table: a gather per table entry, no N x N round trip through global memory, no second kernel
-  fold_bias_to_table<WS, NWARP>(sacc, dtab, h, g.heads, rg, tid, nthreads);
+  if constexpr (FOLD2 && WS == 16) fold_bias_to_table16<NWARP>(sacc, dtab, h, g.heads, rg, tid, nthreads);
+  else fold_bias_to_table<WS, NWARP>(sacc, dtab, h, g.heads, rg, tid, nthreads);
   acc_alpha = warp_sum(acc_alpha);
   if (lane == 0) atomicAdd(dalpha + h, acc_alpha);
   // query-bias gradient: sum over the 8 row groups of the warp (lanes with equal cq), then one atomic per column
@@ -979,7 +1014,20 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
     SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<WS, HD, NWARP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::smem));
     done = true;
   }
-  auto k1 = g.shift > 0 ? attn_bwd_dq_kernel<WS, HD, NWARP, true> : attn_bwd_dq_kernel<WS, HD, NWARP, false>;
+  void (*k1)(const bf16*, const bf16*, const bf16*, const float*, const float*, const float*, bf16*, float*, float*, float*,
+             WinGeom, int, int) = g.shift > 0 ? attn_bwd_dq_kernel<WS, HD, NWARP, true> : attn_bwd_dq_kernel<WS, HD, NWARP, false>;
+  if constexpr (WS == 16) {
+    const char* ev = getenv("SCOT_ATTN_DQ_FOLD2");  // candidate, read per launch
+    if (ev != nullptr && ev[0] == '1') {
+      static bool done2 = false;
+      if (!done2) {
+        SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<WS, HD, NWARP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::smem));
+        SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<WS, HD, NWARP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::smem));
+        done2 = true;
+      }
+      k1 = g.shift > 0 ? attn_bwd_dq_kernel<WS, HD, NWARP, true, true> : attn_bwd_dq_kernel<WS, HD, NWARP, false, true>;
+    }
+  }
   auto k2 = g.shift > 0 ? attn_bwd_dkv_kernel<WS, HD, NWARP, true> : attn_bwd_dkv_kernel<WS, HD, NWARP, false>;
   // dq kernel: ~200 KB of smem -> one CTA per SM, so size the grid to a single wave; fewer chunks also means
   // fewer bias-gradient dumps for the second-stage reduction
