@@ -1,10 +1,10 @@
 """A/B check of the engine's side-branch scheduling knobs on a GPU (not a test: prints a report).
 
-  python scripts/ab_overlap.py [model=B] [batch=64] [steps=20]
+  python scripts/ab_overlap.py [model=B] [batch=64] [steps=20] [settings=defaults,inline,cnx_only,attn_only]
 
 Builds one engine per knob setting (the knobs are read from the environment when an engine first runs), feeds all of
 them the same seeded batch and weights, and compares prediction (must be bit-identical: the forward pass has no
-atomics), loss and the flat gradient (atomics reorder: ~1e-6 relative) against the in-line engine; then times CUDA-graph
+atomics), loss and the flat gradient (atomics reorder: ~1e-6 relative) against the first setting (the defaults); then times CUDA-graph
 replays of zero-grad + forward + backward.
 """
 import json
@@ -19,20 +19,28 @@ from bench import model_config, realistic_init_  # noqa: E402
 from poseidon_b200.runtime import GraphedTrainStep  # noqa: E402
 from poseidon_b200.scOT.model import ScOT, ScOTConfig  # noqa: E402
 
-OFF = {"SCOT_CNX_OVERLAP": "0", "SCOT_ATTN_BWD_SPLIT": "0"}
+OFF = {"SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "16", "SCOT_GEMM_ASYNC_V2": "0", "SCOT_ATTN_DQ_FOLD2": "0"}
 SETTINGS = [
-    ("inline", {}),
-    ("cnx", {"SCOT_CNX_OVERLAP": "1"}),
-    ("attn8", {"SCOT_ATTN_BWD_SPLIT": "8"}),
-    ("attn16", {"SCOT_ATTN_BWD_SPLIT": "16"}),
-    ("defaults", {"SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "16"}),
+    ("defaults", {}),  # must stay first: the reference everything else is compared with
+    ("inline", {"SCOT_CNX_OVERLAP": "0", "SCOT_ATTN_BWD_SPLIT": "0"}),
+    ("cnx_only", {"SCOT_ATTN_BWD_SPLIT": "0"}),
+    ("attn_only", {"SCOT_CNX_OVERLAP": "0"}),
+    # round-2 candidates (never run on hardware when this was written): run them one per process under a timeout,
+    # e.g.  timeout 120 python scripts/ab_overlap.py B 64 20 defaults,gemm_v2
+    ("gemm_v2", {"SCOT_GEMM_ASYNC_V2": "1"}),
+    ("gemm_v2_2g", {"SCOT_GEMM_ASYNC_V2": "3"}),
+    ("gemm_v2_smallk", {"SCOT_GEMM_ASYNC_V2": "5"}),
+    ("gemm_v2_all", {"SCOT_GEMM_ASYNC_V2": "7"}),
+    ("dq_fold2", {"SCOT_ATTN_DQ_FOLD2": "1"}),
 ]
+DEFAULT_RUN = ("defaults", "inline", "cnx_only", "attn_only")
 
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "B"
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+    chosen = tuple(sys.argv[4].split(",")) if len(sys.argv) > 4 else DEFAULT_RUN
     dev = torch.device("cuda", 0)
     cfg = model_config(name, 5)
     gen = torch.Generator().manual_seed(7)
@@ -42,7 +50,7 @@ def main():
     ht = torch.rand(batch, generator=gen)
     ref = None
     report = []
-    for label, env in SETTINGS:
+    for label, env in [x for x in SETTINGS if x[0] in chosen]:
         os.environ.update(OFF)
         os.environ.update(env)
         torch.manual_seed(0)
@@ -86,7 +94,7 @@ def main():
         del model
         torch.cuda.empty_cache()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"ab_overlap_{name}{batch}.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", f"ab_overlap_{name}{batch}_{chosen[-1]}.json"), "w") as f:
         json.dump(report, f, indent=1)
 
 
