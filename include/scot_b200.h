@@ -28,13 +28,18 @@
 extern "C" {
 #endif
 
-#define SCOT_ABI_VERSION 1
+#define SCOT_ABI_VERSION 2
 
 /* ---- library ------------------------------------------------------------------------------------ */
 int scot_abi_version(void);
 const char* scot_last_error(void);
 /* number of kernels launched by this library since process start (bench.py's `gpu_launches`) */
 unsigned long long scot_launch_count(void);
+/* "parity" precision (split-bf16) for the per-op entry points below: when bytes != 0 every bf16 tensor T passed to them is
+ * a pair -- T itself holds hi = bf16(x), and the tensor `bytes` bytes after T holds lo = bf16(x - hi) -- GEMMs accumulate
+ * A_hi B_hi + A_hi B_lo + A_lo B_hi on the tensor cores, attention runs in fp32. Thread local; 0 restores plain bf16.
+ * The whole-model engine selects the mode through ScotModelDesc.precision and manages the offset itself. */
+void scot_set_split_offset(size_t bytes);
 
 /* ---- GEMM (tcgen05 / TMA) ------------------------------------------------------------------------
  * D[m,n] = sum_k A(m,k) * B(n,k), bf16 operands, fp32 accumulation.
@@ -137,6 +142,9 @@ typedef struct ScotModelDesc {
   int n_slices;   /* 0: plain l1/mse; else len(channel_slice_list_normalized_loss) */
   int slices[10];
   float layer_norm_eps;
+  int precision; /* 0: bf16 operands (speed mode). 1: "parity" mode -- split-bf16 operands (3 tensor-core passes per GEMM),
+                  * fp32 attention: the reference trains in fp32 (scOT/train.py:311) and this mode meets 1e-3 against it.
+                  * The workspace doubles (every bf16 tensor gets its lo twin). */
 } ScotModelDesc;
 
 typedef struct ScotEngine ScotEngine;

@@ -47,6 +47,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     lib.scot_abi_version.restype = C.c_int
     lib.scot_last_error.restype = C.c_char_p
     lib.scot_launch_count.restype = C.c_ulonglong
+    lib.scot_set_split_offset.argtypes = [C.c_size_t]
+    lib.scot_set_split_offset.restype = None
     _declare(lib)
     _lib = lib
     return lib
@@ -62,6 +64,22 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().scot_last_error().decode(errors="replace")
         raise RuntimeError(f"libscot_b200 {what} failed (rc={rc}): {msg}")
+
+
+class split_offset:
+    """Context manager for the per-op entry points in "parity" (split-bf16) precision: inside it every bf16 tensor T
+    passed to the library is the pair (T, tensor `nbytes` bytes after T); see scot_set_split_offset in scot_b200.h."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+
+    def __enter__(self):
+        load().scot_set_split_offset(self.nbytes)
+        return self
+
+    def __exit__(self, *exc):
+        load().scot_set_split_offset(0)
+        return False
 
 
 def ptr(t):
@@ -97,6 +115,7 @@ class ScotModelDesc(C.Structure):
         ("window_size", C.c_int), ("mlp_ratio", C.c_float),
         ("use_conditioning", C.c_int), ("learn_residual", C.c_int), ("loss_p", C.c_int),
         ("n_slices", C.c_int), ("slices", C.c_int * 10), ("layer_norm_eps", C.c_float),
+        ("precision", C.c_int),
     ]
 
 

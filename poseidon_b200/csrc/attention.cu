@@ -1130,6 +1130,8 @@ int scot_attn_fwd_launch(const void* qkv, void* out, float* lse, const float* ta
                          int res, int ws, int shift, int heads, int hd, cudaStream_t st) {
   SCOT_REQUIRE(qkv && out && lse && tab2 && alpha, "attn_fwd: null pointer");
   SCOT_REQUIRE(res % ws == 0 && (shift == 0 || shift == ws / 2), "attn_fwd: bad geometry res=%d ws=%d shift=%d", res, ws, shift);
+  if (const size_t lo = scot_split_off())  // "parity" precision: fp32 attention on the split-bf16 tensors
+    return scot_attn32_fwd_launch(qkv, out, lse, tab2, alpha, batch, res, ws, shift, heads, hd, lo, st);
   WinGeom g{res, shift, res / ws, heads, heads * hd};
   const int tw = batch * g.nws * g.nws;
   ATTN_DISPATCH(16, 16, (launch_fwd<16, 16>(qkv, out, lse, tab2, alpha, g, tw, st)))
@@ -1158,6 +1160,9 @@ int scot_attn_bwd_launch2(const void* qkv, const void* o, const void* d_o, const
                           cudaStream_t st, const ScotAttnBwdFork* fk) {
   SCOT_REQUIRE(qkv && o && d_o && lse && tab2 && alpha && dqkv && dtab && dalpha, "attn_bwd: null pointer");
   SCOT_REQUIRE(fk == nullptr || (fk->stream != nullptr && fk->fork != nullptr && fk->join != nullptr), "attn_bwd: bad fork descriptor");
+  if (const size_t lo = scot_split_off())
+    return scot_attn32_bwd_launch(qkv, o, d_o, lse, tab2, alpha, dqkv, dtab, dalpha, g_qbias, g_vbias, batch, res, ws, shift,
+                                  heads, hd, lo, st);
   WinGeom g{res, shift, res / ws, heads, heads * hd};
   const int tw = batch * g.nws * g.nws;
 #define BWD_ARGS qkv, o, d_o, lse, tab2, alpha, dqkv, partial, partial_bytes, dtab, dalpha, g_qbias, g_vbias, g, tw, st, fk

@@ -18,6 +18,9 @@ void scot_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void scot_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static thread_local size_t g_split_off = 0;
+size_t scot_split_off() { return g_split_off; }
+void scot_set_split_off(size_t bytes) { g_split_off = bytes; }
 bool scot_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -32,6 +35,7 @@ extern "C" {
 int scot_abi_version(void) { return SCOT_ABI_VERSION; }
 const char* scot_last_error(void) { return g_err; }
 unsigned long long scot_launch_count(void) { return g_launches.load(); }
+void scot_set_split_offset(size_t bytes) { scot_set_split_off(bytes); }
 
 int scot_gemm_bf16(const void* A, long lda, int a_mn_major, const void* B, long ldb, int b_mn_major, int M, int N,
                    int K, const ScotEpilogue* epi, int impl, void* stream) {

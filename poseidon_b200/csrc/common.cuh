@@ -13,6 +13,11 @@ typedef __nv_bfloat16 bf16;
 // ------------------------------------------------------------------------------------------------
 void scot_set_error(const char* fmt, ...);
 void scot_count_launch();
+// "parity" precision (split-bf16): every bf16 tensor T of the hot path has a twin holding bf16(x - float(bf16(x))) that
+// lives `scot_split_off()` bytes after T (0 = plain bf16 mode). Thread-local; the engine sets it for the duration of one
+// forward / backward call, the per-op C ABI through scot_set_split_offset().
+size_t scot_split_off();
+void scot_set_split_off(size_t bytes);
 #define SCOT_CHECK_CUDA(expr)                                                                  \
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \
@@ -105,6 +110,11 @@ __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
   cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;                  // Phi(x)
   pdf = 0.39894228040143267794f * e2;                             // phi(x)
 }
+// full-precision variant for the split-bf16 ("parity") mode: libm erff / expf (a few ulp)
+__device__ __forceinline__ void gelu_parts_precise(float x, float& cdf, float& pdf) {
+  cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   float cdf, pdf;
   gelu_parts(x, cdf, pdf);
@@ -131,6 +141,41 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(t);
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ---- split-bf16 ("parity" precision) loads / stores: value = hi + lo, lo tensor `lo_off` bytes after hi (0 = none) ----
+__device__ __forceinline__ uint32_t split_lo_pack(float a, float b, uint32_t hi) {
+  const float2 h = unpack_bf16x2(hi);
+  return pack_bf16x2(a - h.x, b - h.y);
+}
+// stores 4 consecutive bf16 (8-byte aligned) and returns the value as stored (hi, or hi + lo)
+__device__ __forceinline__ float4 st_bf16x4(bf16* p, size_t lo_off, float a, float b, float c, float d) {
+  const uint2 h = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+  *reinterpret_cast<uint2*>(p) = h;
+  const float2 h01 = unpack_bf16x2(h.x), h23 = unpack_bf16x2(h.y);
+  if (lo_off == 0) return make_float4(h01.x, h01.y, h23.x, h23.y);
+  const uint2 l = make_uint2(pack_bf16x2(a - h01.x, b - h01.y), pack_bf16x2(c - h23.x, d - h23.y));
+  *reinterpret_cast<uint2*>(reinterpret_cast<char*>(p) + lo_off) = l;
+  const float2 l01 = unpack_bf16x2(l.x), l23 = unpack_bf16x2(l.y);
+  return make_float4(h01.x + l01.x, h01.y + l01.y, h23.x + l23.x, h23.y + l23.y);
+}
+__device__ __forceinline__ float4 ld_bf16x4(const bf16* p, size_t lo_off) {
+  const uint2 h = *reinterpret_cast<const uint2*>(p);
+  const float2 h01 = unpack_bf16x2(h.x), h23 = unpack_bf16x2(h.y);
+  if (lo_off == 0) return make_float4(h01.x, h01.y, h23.x, h23.y);
+  const uint2 l = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(p) + lo_off);
+  const float2 l01 = unpack_bf16x2(l.x), l23 = unpack_bf16x2(l.y);
+  return make_float4(h01.x + l01.x, h01.y + l01.y, h23.x + l23.x, h23.y + l23.y);
+}
+__device__ __forceinline__ void st_bf16(bf16* p, size_t lo_off, float v) {
+  const bf16 h = __float2bfloat16_rn(v);
+  *p = h;
+  if (lo_off) *reinterpret_cast<bf16*>(reinterpret_cast<char*>(p) + lo_off) = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ float ld_bf16(const bf16* p, size_t lo_off) {
+  float v = __bfloat162float(*p);
+  if (lo_off) v += __bfloat162float(*reinterpret_cast<const bf16*>(reinterpret_cast<const char*>(p) + lo_off));
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // mbarrier

@@ -78,6 +78,7 @@ struct ScotEngine {
   long rec_w, rec_b, rec_mix;
   // arena plan
   size_t ws_bytes = 0;
+  size_t split_off = 0;  // parity precision: byte distance hi -> lo twin of every bf16 arena tensor (a shadow arena)
   size_t wb16;  // bf16 copy of the flat parameters
   size_t p16, emb_zhat, emb_rstd, emb_x, emb_xb;
   std::vector<std::vector<BlockBuf>> ebuf, dbuf;
@@ -426,6 +427,11 @@ int build_plan(ScotEngine* e) {
     }
   }
   e->ws_bytes = b.off;
+  if (e->d.precision == 1) {
+    // shadow arena: the lo twin of the bf16 tensor at offset X lives at X + split_off (fp32 tensors leave theirs unused)
+    e->split_off = (b.off + 255) & ~size_t(255);
+    e->ws_bytes = 2 * e->split_off;
+  }
   return 0;
 }
 
@@ -445,6 +451,12 @@ struct Ctx {
   const bf16* w16(long off) const { return reinterpret_cast<const bf16*>(A + e->wb16) + off; }
   const float* p(long off) const { return off < 0 ? nullptr : P + off; }
   float* g(long off) const { return off < 0 ? nullptr : G + off; }
+};
+
+// sets the thread-local split offset for the duration of one engine call
+struct SplitGuard {
+  explicit SplitGuard(size_t off) { scot_set_split_off(off); }
+  ~SplitGuard() { scot_set_split_off(0); }
 };
 
 #define RC(expr)                 \
@@ -683,6 +695,7 @@ int scot_engine_create(const ScotModelDesc* desc, int batch, ScotEngine** out) {
   SCOT_REQUIRE(d.num_stages >= 1 && d.num_stages <= 4, "engine_create: 1..4 stages supported (got %d)", d.num_stages);
   SCOT_REQUIRE(d.image_size % d.patch_size == 0, "engine_create: image_size must be a multiple of patch_size");
   SCOT_REQUIRE(d.mlp_ratio > 0.f, "engine_create: mlp_ratio");
+  SCOT_REQUIRE(d.precision == 0 || d.precision == 1, "engine_create: precision must be 0 (bf16) or 1 (parity / split-bf16)");
   SCOT_REQUIRE(d.num_out_channels * d.num_out_channels * 25 <= 1024, "engine_create: at most 6 output channels");
   ScotEngine* e = new ScotEngine();
   e->d = d;
@@ -772,6 +785,7 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
   SCOT_REQUIRE(labels == nullptr || loss_out != nullptr, "engine_forward: loss_out required with labels");
   SCOT_REQUIRE(((uintptr_t)arena & 255) == 0 && ((uintptr_t)params & 15) == 0, "engine_forward: arena must be 256 B aligned");
   Ctx c{e, params, nullptr, (uint8_t*)arena, time, (cudaStream_t)stream, gemm_impl};
+  SplitGuard split_guard(e->split_off);
   const int B = e->batch, ns = e->ns;
   const Geo& g0 = e->geo[0];
   RC(cnx_side_init(e));
@@ -902,6 +916,7 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
   SCOT_REQUIRE(grad_loss == nullptr || e->last_labels != nullptr, "engine_backward: grad_loss given but forward had no labels");
   const ScotModelDesc& d = e->d;
   Ctx c{e, params, grads, (uint8_t*)arena, e->last_time, (cudaStream_t)stream, gemm_impl};
+  SplitGuard split_guard(e->split_off);
   const int B = e->batch, ns = e->ns;
   const Geo& g0 = e->geo[0];
   const int NR = d.num_out_channels * d.patch_size * d.patch_size;

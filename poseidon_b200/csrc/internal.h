@@ -33,6 +33,13 @@ int scot_attn_bwd_launch2(const void* qkv, const void* o, const void* d_o, const
                           const float* alpha, void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha,
                           float* g_qbias, float* g_vbias, int batch, int res, int ws, int shift, int heads, int hd,
                           cudaStream_t st, const ScotAttnBwdFork* fk);
+// attention_f32.cu: fp32 CUDA-core attention of the "parity" precision mode (operands are hi + lo bf16 pairs, the lo
+// tensors `lo_off` bytes after the hi ones; lo_off = 0 reads / writes plain bf16)
+int scot_attn32_fwd_launch(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, int batch, int res,
+                           int ws, int shift, int heads, int hd, size_t lo_off, cudaStream_t st);
+int scot_attn32_bwd_launch(const void* qkv, const void* o, const void* d_o, const float* lse, const float* tab2,
+                           const float* alpha, void* dqkv, float* dtab, float* dalpha, float* g_qbias, float* g_vbias,
+                           int batch, int res, int ws, int shift, int heads, int hd, size_t lo_off, cudaStream_t st);
 // misc.cu
 int scot_cast_f32_bf16_launch(const float* in, void* out, long n, cudaStream_t st);
 int scot_expand_bias_launch(const float* bias, float* out, int n, int rep, cudaStream_t st);

@@ -12,11 +12,11 @@ constexpr int kThreads = 256;
 inline unsigned blocks_for(long n, int per = kThreads) { return (unsigned)((n + per - 1) / per); }
 
 // ---- casts / elementwise -----------------------------------------------------------------------------
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long n4) {
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long n4, size_t lo_off) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = reinterpret_cast<const float4*>(in)[i];
-  reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  st_bf16x4(out + 4 * i, lo_off, v.x, v.y, v.z, v.w);
 }
 
 __global__ void expand_bias_kernel(const float* __restrict__ bias, float* __restrict__ out, int n, int rep) {
@@ -26,7 +26,7 @@ __global__ void expand_bias_kernel(const float* __restrict__ bias, float* __rest
 
 // ---- patch embedding im2col: [B,Cin,H,W] fp32 -> [B*(H/ps)*(W/ps), Cin*ps*ps] bf16, k = (c, di, dj) ------
 __global__ void im2col_patch_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int H, int W,
-                                    int ps) {
+                                    int ps, size_t lo_off) {
   const int gw = W / ps, gh = H / ps;
   const long total = (long)B * gh * gw * Cin * ps;  // one thread per (token, c, di): ps contiguous pixels
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,13 +41,13 @@ __global__ void im2col_patch_kernel(const float* __restrict__ x, bf16* __restric
   const int b = (int)(t / gh);
   const float* src = x + (((long)b * Cin + c) * H + (ii * ps + di)) * W + j * ps;
   bf16* dst = out + (((long)b * gh + ii) * gw + j) * (Cin * ps * ps) + (c * ps + di) * ps;
-  for (int dj = 0; dj < ps; ++dj) dst[dj] = __float2bfloat16_rn(src[dj]);
+  for (int dj = 0; dj < ps; ++dj) st_bf16(dst + dj, lo_off, src[dj]);
 }
 
 // ---- patch merging ------------------------------------------------------------------------------------
 // out[b, (i,j), q*C + c] = x[b, 2i+(q&1), 2j+(q>>1), c] + inp[...]   q = 0..3 -> (0,0),(1,0),(0,1),(1,1)
 __global__ void merge_gather_kernel(const float* __restrict__ x, const float* __restrict__ inp, bf16* __restrict__ out,
-                                    int B, int res, int C) {
+                                    int B, int res, int C, size_t lo_off) {
   const int c4n = C / 4, r2 = res / 2;
   const long total = (long)B * r2 * r2 * 4 * c4n;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,8 +66,7 @@ __global__ void merge_gather_kernel(const float* __restrict__ x, const float* __
     const float4 w = *reinterpret_cast<const float4*>(inp + src);
     v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
   }
-  *reinterpret_cast<uint2*>(out + (((long)b * r2 + ii) * r2 + j) * (4L * C) + q * C + c4 * 4) =
-      make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  st_bf16x4(out + (((long)b * r2 + ii) * r2 + j) * (4L * C) + q * C + c4 * 4, lo_off, v.x, v.y, v.z, v.w);
 }
 // g_out[b,(y,x),c] = (g_in ? g_in : 0) + dG[b,(y/2,x/2), q*C + c]   (inverse of the gather)
 __global__ void merge_scatter_kernel(const float* __restrict__ dG, const float* __restrict__ g_in, float* __restrict__ g_out,
@@ -95,7 +94,7 @@ __global__ void merge_scatter_kernel(const float* __restrict__ dG, const float* 
 // ---- ConvNeXt layer scale residual ---------------------------------------------------------------------
 // out = in + gamma * z ; zb = bf16(z) saved for the gamma gradient
 __global__ void scale_add_fwd_kernel(const float* __restrict__ in, const float* __restrict__ z, const float* __restrict__ gamma,
-                                     float* __restrict__ out, bf16* __restrict__ zb, long rows, int C) {
+                                     float* __restrict__ out, bf16* __restrict__ zb, long rows, int C, size_t lo_off) {
   const int c4n = C / 4;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * c4n) return;
@@ -104,7 +103,7 @@ __global__ void scale_add_fwd_kernel(const float* __restrict__ in, const float* 
   const float4 gm = *reinterpret_cast<const float4*>(gamma + c4 * 4);
   reinterpret_cast<float4*>(out)[i] =
       make_float4(fmaf(gm.x, zz.x, a.x), fmaf(gm.y, zz.y, a.y), fmaf(gm.z, zz.z, a.z), fmaf(gm.w, zz.w, a.w));
-  reinterpret_cast<uint2*>(zb)[i] = make_uint2(pack_bf16x2(zz.x, zz.y), pack_bf16x2(zz.z, zz.w));
+  st_bf16x4(zb + 4 * i, lo_off, zz.x, zz.y, zz.z, zz.w);
 }
 // dz = gamma * g (bf16); g_gamma[c] += sum_m g*z ; g_bias[c] += sum_m dz.
 // A block sweeps `rows_per_block` rows; thread = (row phase, 4 channels) with every thread active for any C (256 / (C/4)
@@ -112,7 +111,7 @@ __global__ void scale_add_fwd_kernel(const float* __restrict__ in, const float* 
 __global__ void __launch_bounds__(256)
 scale_add_bwd_kernel(const float* __restrict__ g, const bf16* __restrict__ zb, const float* __restrict__ gamma,
                      bf16* __restrict__ dz, float* __restrict__ g_gamma, float* __restrict__ g_bias, long rows, int C,
-                     int rows_per_block) {
+                     int rows_per_block, size_t lo_off) {
   extern __shared__ float4 sab_red[];  // [rpp][c4n][2]
   const int c4n = C / 4;
   const int rpp = 256 / c4n;  // rows per pass
@@ -126,13 +125,10 @@ scale_add_bwd_kernel(const float* __restrict__ g, const bf16* __restrict__ zb, c
 #pragma unroll 4
     for (long row = row0 + rsub; row < row1; row += rpp) {
       const float4 gv = *reinterpret_cast<const float4*>(g + row * C + c4 * 4);
-      const uint2 zr = *reinterpret_cast<const uint2*>(zb + row * C + c4 * 4);
-      const float2 z01 = unpack_bf16x2(zr.x), z23 = unpack_bf16x2(zr.y);
-      sg.x += gv.x * z01.x; sg.y += gv.y * z01.y; sg.z += gv.z * z23.x; sg.w += gv.w * z23.y;
-      const uint2 o = make_uint2(pack_bf16x2(gm.x * gv.x, gm.y * gv.y), pack_bf16x2(gm.z * gv.z, gm.w * gv.w));
-      *reinterpret_cast<uint2*>(dz + row * C + c4 * 4) = o;
-      const float2 d01 = unpack_bf16x2(o.x), d23 = unpack_bf16x2(o.y);
-      sb.x += d01.x; sb.y += d01.y; sb.z += d23.x; sb.w += d23.y;
+      const float4 zr = ld_bf16x4(zb + row * C + c4 * 4, lo_off);
+      sg.x += gv.x * zr.x; sg.y += gv.y * zr.y; sg.z += gv.z * zr.z; sg.w += gv.w * zr.w;
+      const float4 d = st_bf16x4(dz + row * C + c4 * 4, lo_off, gm.x * gv.x, gm.y * gv.y, gm.z * gv.z, gm.w * gv.w);
+      sb.x += d.x; sb.y += d.y; sb.z += d.z; sb.w += d.w;
     }
     sab_red[(rsub * c4n + c4) * 2 + 0] = sg;
     sab_red[(rsub * c4n + c4) * 2 + 1] = sb;
@@ -292,7 +288,7 @@ __global__ void unshuffle_kernel(const float* __restrict__ D, float* __restrict_
 }
 // planar gradient -> token-major bf16 [tokens, OC*ps*ps] + ConvTranspose2d bias gradient (sum per channel)
 __global__ void shuffle_grad_kernel(const float* __restrict__ dP, bf16* __restrict__ dD, float* __restrict__ g_bias, int B,
-                                    int OC, int H, int W, int ps) {
+                                    int OC, int H, int W, int ps, size_t lo_off) {
   const long total = (long)B * OC * H * W;
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   float val = 0.f;
@@ -304,9 +300,9 @@ __global__ void shuffle_grad_kernel(const float* __restrict__ dP, bf16* __restri
     t /= H;
     c = (int)(t % OC);
     const int b = (int)(t / OC);
-    const bf16 r = __float2bfloat16_rn(dP[i]);
-    dD[(((long)b * (H / ps) + y / ps) * (W / ps) + x / ps) * (OC * ps * ps) + (c * ps + (y % ps)) * ps + (x % ps)] = r;
-    val = __bfloat162float(r);
+    bf16* dst = dD + (((long)b * (H / ps) + y / ps) * (W / ps) + x / ps) * (OC * ps * ps) + (c * ps + (y % ps)) * ps + (x % ps);
+    st_bf16(dst, lo_off, dP[i]);
+    val = ld_bf16(dst, lo_off);
   }
   // H*W is a multiple of the block size, so a block never straddles two channels
   __shared__ float sred[kThreads / 32];
@@ -540,7 +536,7 @@ __global__ void loss_bwd_kernel(const float* __restrict__ pred, const float* __r
 
 int scot_cast_f32_bf16_launch(const float* in, void* out, long n, cudaStream_t st) {
   SCOT_REQUIRE(n % 4 == 0, "cast: n must be a multiple of 4");
-  cast_f32_bf16_kernel<<<blocks_for(n / 4), kThreads, 0, st>>>(in, (bf16*)out, n / 4);
+  cast_f32_bf16_kernel<<<blocks_for(n / 4), kThreads, 0, st>>>(in, (bf16*)out, n / 4, scot_split_off());
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -552,13 +548,13 @@ int scot_expand_bias_launch(const float* bias, float* out, int n, int rep, cudaS
 int scot_im2col_patch_launch(const float* x, void* out, int B, int Cin, int H, int W, int ps, cudaStream_t st) {
   SCOT_REQUIRE(H % ps == 0 && W % ps == 0, "im2col: image size must be a multiple of the patch size");
   const long total = (long)B * (H / ps) * (W / ps) * Cin * ps;
-  im2col_patch_kernel<<<blocks_for(total), kThreads, 0, st>>>(x, (bf16*)out, B, Cin, H, W, ps);
+  im2col_patch_kernel<<<blocks_for(total), kThreads, 0, st>>>(x, (bf16*)out, B, Cin, H, W, ps, scot_split_off());
   SCOT_LAUNCH_CHECK();
   return 0;
 }
 int scot_merge_gather_launch(const float* x, const float* inp, void* out, int B, int res, int C, cudaStream_t st) {
   SCOT_REQUIRE(res % 2 == 0 && C % 4 == 0, "merge_gather: res must be even");
-  merge_gather_kernel<<<blocks_for((long)B * res * res * (C / 4)), kThreads, 0, st>>>(x, inp, (bf16*)out, B, res, C);
+  merge_gather_kernel<<<blocks_for((long)B * res * res * (C / 4)), kThreads, 0, st>>>(x, inp, (bf16*)out, B, res, C, scot_split_off());
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -569,7 +565,7 @@ int scot_merge_scatter_launch(const float* dG, const float* g_in, float* g_out, 
 }
 int scot_scale_add_fwd_launch(const float* in, const float* z, const float* gamma, float* out, void* zb, long rows, int C,
                               cudaStream_t st) {
-  scale_add_fwd_kernel<<<blocks_for(rows * (C / 4)), kThreads, 0, st>>>(in, z, gamma, out, (bf16*)zb, rows, C);
+  scale_add_fwd_kernel<<<blocks_for(rows * (C / 4)), kThreads, 0, st>>>(in, z, gamma, out, (bf16*)zb, rows, C, scot_split_off());
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -583,7 +579,7 @@ int scot_scale_add_bwd_launch(const float* g, const void* zb, const float* gamma
   rpb = (rpb + rpp - 1) / rpp * rpp;
   const size_t smem = (size_t)rpp * c4n * 2 * sizeof(float4);
   scale_add_bwd_kernel<<<(unsigned)((rows + rpb - 1) / rpb), 256, smem, st>>>(g, (const bf16*)zb, gamma, (bf16*)dz, g_gamma,
-                                                                              g_bias, rows, C, (int)rpb);
+                                                                              g_bias, rows, C, (int)rpb, scot_split_off());
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -648,7 +644,7 @@ int scot_conv5_bwd_launch(const float* P, const float* w, const float* dpred, fl
 #undef C5B
   }
   SCOT_LAUNCH_CHECK();
-  shuffle_grad_kernel<<<blocks_for((long)B * OC * H * W), kThreads, 0, st>>>(dP_scratch, (bf16*)dD, g_bias, B, OC, H, W, ps);
+  shuffle_grad_kernel<<<blocks_for((long)B * OC * H * W), kThreads, 0, st>>>(dP_scratch, (bf16*)dD, g_bias, B, OC, H, W, ps, scot_split_off());
   SCOT_LAUNCH_CHECK();
   return 0;
 }

@@ -30,6 +30,7 @@ struct ClnFwdArgs {
   int rows_per_sample;   // of the OUTPUT row index
   int perm_res;          // 0: r_out = r_in. >0: unmerge pixel shuffle with input grid perm_res x perm_res
   float eps;
+  size_t lo_off;         // split-bf16 ("parity") mode: byte distance of the lo twins of xb_out / zhat (0 = none)
 };
 
 // r_in = ((b*res + i)*res + j)*4 + a*2 + c  ->  r_out = (b*2res + 2i+a)*2res + 2j+c   (model.py:748-754)
@@ -92,11 +93,8 @@ __global__ void __launch_bounds__(256) cln_fwd_kernel(ClnFwdArgs p) {
     if (cv >= nvec) continue;
     const int c0 = cv * 4;
     float zh[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
-    if (p.zhat != nullptr) {
-      // saved for the backward pass in bf16 (the forward output below uses the unrounded fp32 value)
-      uint2 o = make_uint2(pack_bf16x2(zh[0], zh[1]), pack_bf16x2(zh[2], zh[3]));
-      *reinterpret_cast<uint2*>(p.zhat + r_out * p.C + c0) = o;
-    }
+    // saved for the backward pass in bf16 (the forward output below uses the unrounded fp32 value)
+    if (p.zhat != nullptr) st_bf16x4(p.zhat + r_out * p.C + c0, p.lo_off, zh[0], zh[1], zh[2], zh[3]);
     const float4 ab = *reinterpret_cast<const float4*>(p.ab + c0);
     const float4 cb = *reinterpret_cast<const float4*>(p.cb + c0);
     float sc[4] = {ab.x, ab.y, ab.z, ab.w}, sh[4] = {cb.x, cb.y, cb.z, cb.w};
@@ -114,8 +112,7 @@ __global__ void __launch_bounds__(256) cln_fwd_kernel(ClnFwdArgs p) {
       y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
     }
     if (p.x_out != nullptr) *reinterpret_cast<float4*>(p.x_out + r_out * p.C + c0) = make_float4(y[0], y[1], y[2], y[3]);
-    if (p.xb_out != nullptr)
-      *reinterpret_cast<uint2*>(p.xb_out + r_out * p.C + c0) = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
+    if (p.xb_out != nullptr) st_bf16x4(p.xb_out + r_out * p.C + c0, p.lo_off, y[0], y[1], y[2], y[3]);
   }
 }
 
@@ -138,10 +135,12 @@ struct ClnBwdArgs {
   int rows_per_sample;
   int rows_per_block; // divides rows_per_sample
   int perm_res;
+  size_t lo_off;      // split-bf16 ("parity") mode: lo twins of zhat (read) and of a bf16 dz (written)
 };
 
-template <int LPR, int V>
-__global__ void __launch_bounds__(256, (V <= 3 ? 2 : 1)) cln_bwd_kernel(ClnBwdArgs p) {
+// SPLIT: split-bf16 ("parity") mode — zhat is read as hi + lo, a bf16 dz is written as hi + lo
+template <int LPR, int V, bool SPLIT = false>
+__global__ void __launch_bounds__(256, ((V <= 3 && !SPLIT) ? 2 : 1)) cln_bwd_kernel(ClnBwdArgs p) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float red[];  // [warps][5][C]
@@ -179,6 +178,7 @@ __global__ void __launch_bounds__(256, (V <= 3 ? 2 : 1)) cln_bwd_kernel(ClnBwdAr
   for (int rr0 = warp * RPW + sub; rr0 < p.rows_per_block; rr0 += row_stride * R) {
     float4 dy[R][V];
     uint2 zp[R][V];  // normalised input, packed bf16 (unpacked at each use: two ALU ops instead of two more registers)
+    uint2 zl[SPLIT ? R : 1][SPLIT ? V : 1];
     float rs[R], tt[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
@@ -193,9 +193,12 @@ __global__ void __launch_bounds__(256, (V <= 3 ? 2 : 1)) cln_bwd_kernel(ClnBwdAr
         if (cv < nvec && in) {
           dy[k][i] = *reinterpret_cast<const float4*>(p.dy + r_out * p.C + cv * 4);
           zp[k][i] = *reinterpret_cast<const uint2*>(p.zhat + r_out * p.C + cv * 4);
+          if constexpr (SPLIT)
+            zl[k][i] = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(p.zhat + r_out * p.C + cv * 4) + p.lo_off);
         } else {
           dy[k][i] = make_float4(0.f, 0.f, 0.f, 0.f);
           zp[k][i] = make_uint2(0u, 0u);
+          if constexpr (SPLIT) zl[k][i] = make_uint2(0u, 0u);
         }
       }
     }
@@ -207,7 +210,11 @@ __global__ void __launch_bounds__(256, (V <= 3 ? 2 : 1)) cln_bwd_kernel(ClnBwdAr
       const float t = tt[k];
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const float2 z01 = unpack_bf16x2(zp[k][i].x), z23 = unpack_bf16x2(zp[k][i].y);
+        float2 z01 = unpack_bf16x2(zp[k][i].x), z23 = unpack_bf16x2(zp[k][i].y);
+        if constexpr (SPLIT) {
+          const float2 l01 = unpack_bf16x2(zl[k][i].x), l23 = unpack_bf16x2(zl[k][i].y);
+          z01.x += l01.x; z01.y += l01.y; z23.x += l23.x; z23.y += l23.y;
+        }
         const float4 pz = make_float4(dy[k][i].x * z01.x, dy[k][i].y * z01.y, dy[k][i].z * z23.x, dy[k][i].w * z23.y);
         acc_a[i].x += pz.x; acc_a[i].y += pz.y; acc_a[i].z += pz.z; acc_a[i].w += pz.w;
         acc_c[i].x += dy[k][i].x; acc_c[i].y += dy[k][i].y; acc_c[i].z += dy[k][i].z; acc_c[i].w += dy[k][i].w;
@@ -255,7 +262,11 @@ __global__ void __launch_bounds__(256, (V <= 3 ? 2 : 1)) cln_bwd_kernel(ClnBwdAr
       for (int i = 0; i < V; ++i) {
         const int cv = sl + i * LPR;
         if (cv < nvec) {
-          const float2 z01 = unpack_bf16x2(zp[k][i].x), z23 = unpack_bf16x2(zp[k][i].y);
+          float2 z01 = unpack_bf16x2(zp[k][i].x), z23 = unpack_bf16x2(zp[k][i].y);
+          if constexpr (SPLIT) {
+            const float2 l01 = unpack_bf16x2(zl[k][i].x), l23 = unpack_bf16x2(zl[k][i].y);
+            z01.x += l01.x; z01.y += l01.y; z23.x += l23.x; z23.y += l23.y;
+          }
           float4 dz;
           dz.x = (dy[k][i].x - m1 - z01.x * m2) * rstd;
           dz.y = (dy[k][i].y - m1 - z01.y * m2) * rstd;
@@ -264,10 +275,7 @@ __global__ void __launch_bounds__(256, (V <= 3 ? 2 : 1)) cln_bwd_kernel(ClnBwdAr
           if (p.dz_is_f32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dz) + r_in * p.C + cv * 4) = dz;
           } else {
-            const uint2 o = make_uint2(pack_bf16x2(dz.x, dz.y), pack_bf16x2(dz.z, dz.w));
-            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.dz) + r_in * p.C + cv * 4) = o;
-            const float2 a = unpack_bf16x2(o.x), b = unpack_bf16x2(o.y);
-            dz = make_float4(a.x, a.y, b.x, b.y);
+            dz = st_bf16x4(reinterpret_cast<bf16*>(p.dz) + r_in * p.C + cv * 4, SPLIT ? p.lo_off : 0, dz.x, dz.y, dz.z, dz.w);
           }
           acc_b[i].x += dz.x; acc_b[i].y += dz.y; acc_b[i].z += dz.z; acc_b[i].w += dz.w;
         }
@@ -319,8 +327,8 @@ int launch_fwd(const ClnFwdArgs& a, cudaStream_t st) {
   SCOT_LAUNCH_CHECK();
   return 0;
 }
-template <int LPR, int V>
-int launch_bwd(const ClnBwdArgs& a_in, cudaStream_t st) {
+template <int LPR, int V, bool SPLIT>
+int launch_bwd_t(const ClnBwdArgs& a_in, cudaStream_t st) {
   ClnBwdArgs a = a_in;
   const int warps = a.C > 768 ? 4 : 8;  // [warps][5][C] floats of smem must fit 227 KB (C = 1536: Poseidon-L stage 3)
   if (a.rows_per_block <= 0) {
@@ -358,12 +366,16 @@ int launch_bwd(const ClnBwdArgs& a_in, cudaStream_t st) {
   if (!attr_done) {
     constexpr int kMaxC = 4 * LPR * V;
     constexpr int kMaxSmem = (kMaxC > 768 ? 4 : 8) * 5 * kMaxC * 4;
-    SCOT_CHECK_CUDA(cudaFuncSetAttribute(cln_bwd_kernel<LPR, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    SCOT_CHECK_CUDA(cudaFuncSetAttribute(cln_bwd_kernel<LPR, V, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_done = true;
   }
-  SCOT_CHECK_CUDA(scot_launch_pdl(cln_bwd_kernel<LPR, V>, dim3((unsigned)blocks), dim3(warps * 32), smem, st, a));
+  SCOT_CHECK_CUDA(scot_launch_pdl(cln_bwd_kernel<LPR, V, SPLIT>, dim3((unsigned)blocks), dim3(warps * 32), smem, st, a));
   SCOT_LAUNCH_CHECK();
   return 0;
+}
+template <int LPR, int V>
+int launch_bwd(const ClnBwdArgs& a, cudaStream_t st) {
+  return a.lo_off != 0 ? launch_bwd_t<LPR, V, true>(a, st) : launch_bwd_t<LPR, V, false>(a, st);
 }
 
 }  // namespace
@@ -394,7 +406,7 @@ int scot_cln_fwd_launch(const float* z, const float* residual, const float* time
   SCOT_REQUIRE(aw == nullptr || time != nullptr, "cln_fwd: conditioned norm needs time");
   SCOT_REQUIRE(perm_res == 0 || residual == nullptr, "cln_fwd: residual not supported with permutation");
   ClnFwdArgs a{z, residual, time, aw, ab, cw, cb, x_out, (bf16*)xb_out, (bf16*)zhat, rstd, rows, C, rows_per_sample,
-               perm_res, eps};
+               perm_res, eps, scot_split_off()};
   CLN_DISPATCH(launch_fwd, a);
 }
 
@@ -415,6 +427,6 @@ int scot_cln_bwd_launch(const float* dy, const void* zhat, const float* rstd, co
     if (override_rpb > 0) rpb = override_rpb;
   }
   ClnBwdArgs a{dy, (const bf16*)zhat, rstd, time, aw, ab, dz, dz_is_f32, g_aw, g_ab, g_cw, g_cb, g_bias_prev, rows, C,
-               rows_per_sample, (int)rpb, perm_res};
+               rows_per_sample, (int)rpb, perm_res, scot_split_off()};
   CLN_DISPATCH(launch_bwd, a);
 }

@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert len(names) >= 15
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in scot_b200.h but not exported by libscot_b200.so"
-    assert lib.scot_abi_version() == 1
+    assert lib.scot_abi_version() == 2
 
 
 def test_errors_are_reported_not_thrown(lib):

@@ -1,0 +1,244 @@
+"""The north-star tolerance (GPU): `precision="parity"` — split-bf16 GEMM operands (three tcgen05 passes:
+A_hi B_hi + A_hi B_lo + A_lo B_hi), fp32 attention, hi/lo twins of every saved bf16 tensor — must reproduce the
+UNMODIFIED fp32 reference (fixtures in tests/golden, reference trains in fp32: scOT/train.py:311) to
+
+    output relative L2 < 1e-3,  loss relative < 1e-4                      (BASELINE.json north_star)
+
+and every parameter gradient of the fp64 oracle to a global relative L2 < 2e-3 with no per-tensor outlier.
+The per-op tests pin the two building blocks (split GEMM, fp32 window attention) against fp64 torch.
+"""
+import math
+import os
+import types
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import scot_oracle as O
+from oracle.weights import make_inputs, make_weights
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-300))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from poseidon_b200 import _lib
+
+    _lib.load()
+    return _lib
+
+
+class SplitPool:
+    """bf16 tensors with their lo twins a fixed byte distance behind them (the layout scot_set_split_offset expects)"""
+
+    def __init__(self, nbytes):
+        self.nbytes = (nbytes + 255) // 256 * 256
+        self.buf = torch.zeros(2, self.nbytes, dtype=torch.uint8, device=dev)
+        self.cur = 0
+
+    def alloc(self, *shape):
+        n = 1
+        for s in shape:
+            n *= s
+        off = self.cur
+        self.cur += (2 * n + 255) // 256 * 256
+        assert self.cur <= self.nbytes
+        return self.buf[0, off:off + 2 * n].view(torch.bfloat16).view(*shape)
+
+    def lo(self, t):
+        off = t.data_ptr() - self.buf.data_ptr()
+        return self.buf[1, off:off + 2 * t.numel()].view(torch.bfloat16).view(t.shape)
+
+    def put(self, x):
+        """stores fp32 x as hi + lo, returns the hi tensor"""
+        t = self.alloc(*x.shape)
+        hi = x.float().bfloat16()
+        t.copy_(hi)
+        self.lo(t).copy_((x.float() - hi.float()).bfloat16())
+        return t
+
+    def get(self, t):
+        return t.float() + self.lo(t).float()
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(1000, 288, 96), (4096, 384, 96), (512, 96, 384), (256, 768, 3072)])
+def test_split_gemm_forward_modes(L, impl, M, N, K):
+    torch.manual_seed(M + N + K)
+    pool = SplitPool(64 << 20)
+    A32 = torch.randn(M, K, device=dev)
+    B32 = torch.randn(N, K, device=dev) / K ** 0.5
+    bias = torch.randn(N, device=dev)
+    A, B = pool.put(A32), pool.put(B32)
+    assert rel(pool.get(A), A32) < 1e-5
+    ref = A32.double() @ B32.double().t() + bias.double()
+    out = torch.empty(M, N, device=dev)
+    with L.split_offset(pool.nbytes):
+        L.gemm(A, B, M, N, K, mode=L.EPI_F32, bias=bias, out0=out, impl=impl)
+    assert rel(out, ref) < 2e-5, "fp32 output"
+    ob = pool.alloc(M, N)
+    with L.split_offset(pool.nbytes):
+        L.gemm(A, B, M, N, K, mode=L.EPI_BF16, bias=bias, out0=ob, impl=impl)
+    assert rel(pool.get(ob), ref) < 2e-5, "split bf16 output"
+    gp, g = pool.alloc(M, N), pool.alloc(M, N)
+    with L.split_offset(pool.nbytes):
+        L.gemm(A, B, M, N, K, mode=L.EPI_GELU, bias=bias, out0=gp, out1=g, impl=impl)
+    h = ref.clone().requires_grad_(True)
+    gr = F.gelu(h)
+    gr.sum().backward()
+    assert rel(pool.get(g), gr) < 2e-5 and rel(pool.get(gp), h.grad) < 2e-5, "gelu / gelu'"
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_split_gemm_dgrad_wgrad(L, impl):
+    torch.manual_seed(5)
+    pool = SplitPool(64 << 20)
+    M, N, K = 4096, 96, 384
+    dY32 = torch.randn(M, K, device=dev)
+    W32 = torch.randn(K, N, device=dev) / K ** 0.5
+    gp32 = torch.rand(M, N, device=dev)
+    dY, W, gp = pool.put(dY32), pool.put(W32), pool.put(gp32)
+    g = torch.randn(M, N, device=dev)
+    g0 = g.clone()
+    with L.split_offset(pool.nbytes):
+        L.gemm(dY, W, M, N, K, b_mn=True, mode=L.EPI_RMW_F32, out0=g, impl=impl)
+    assert rel(g - g0, dY32.double() @ W32.double()) < 2e-5
+    out = pool.alloc(M, N)
+    cs = torch.zeros(N, device=dev)
+    with L.split_offset(pool.nbytes):
+        L.gemm(dY, W, M, N, K, b_mn=True, mode=L.EPI_GELU_BWD, out0=out, aux=gp, colsum=cs, impl=impl)
+    ref = (dY32.double() @ W32.double()) * pool.get(gp).double()
+    assert rel(pool.get(out), ref) < 2e-5
+    assert rel(cs, ref.sum(0)) < 1e-4
+    X32 = torch.randn(M, N, device=dev)
+    X = pool.put(X32)
+    dW = torch.zeros(K, N, device=dev)
+    with L.split_offset(pool.nbytes):
+        L.wgrad_group([(dY, X, dW)], impl=impl)
+    assert rel(dW, dY32.double().t() @ X32.double()) < 2e-5
+
+
+ATTN_CASES = [
+    (2, 32, 16, 8, 3, 32), (3, 16, 16, 0, 6, 32), (3, 8, 8, 0, 12, 32), (5, 4, 4, 0, 24, 32),
+    (2, 32, 16, 8, 3, 16), (2, 16, 8, 4, 2, 16), (2, 32, 16, 0, 3, 64),
+]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_fp32_window_attention(L, case):
+    try:
+        from test_gpu_ops import ref_attention
+    except ImportError:
+        from tests.test_gpu_ops import ref_attention
+
+    Bn, res, ws, shift, heads, hd = case
+    torch.manual_seed(sum(case))
+    C = heads * hd
+    M = Bn * res * res
+    pool = SplitPool(64 << 20)
+    qkv32 = torch.randn(M, 3 * C, device=dev) * 1.5
+    qkv = pool.put(qkv32)
+    w1 = torch.randn(512, 2, device=dev)
+    b1 = torch.randn(512, device=dev) * 0.1
+    w2 = torch.randn(heads, 512, device=dev) / 512 ** 0.5
+    ls = math.log(10.0) + 0.3 * torch.randn(heads, 1, 1, device=dev)
+    cpb = L.CpbLayerBuffers(w1, b1, w2, ls, ws, heads)
+    cpb.forward()
+    nwin = Bn * (res // ws) ** 2
+    out = pool.alloc(M, C)
+    lse = torch.empty(nwin * heads, ws * ws, device=dev)
+    with L.split_offset(pool.nbytes):
+        L.attn_fwd(qkv, out, lse, cpb.tab2, cpb.alpha, Bn, res, ws, shift, heads, hd)
+    leaves = [t.double().requires_grad_(True) for t in (pool.get(qkv), w1, b1, w2, ls)]
+    ref = ref_attention(leaves[0], leaves[1:4], leaves[4], Bn, res, ws, shift, heads, hd)
+    assert rel(pool.get(out), ref) < 3e-5, "attention forward"
+    d_o32 = torch.randn(M, C, device=dev)
+    d_o = pool.put(d_o32)
+    ref.backward(pool.get(d_o).double())
+    dqkv = pool.alloc(M, 3 * C)
+    partial = torch.zeros(64, device=dev)
+    gq, gv = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    with L.split_offset(pool.nbytes):
+        L.attn_bwd(qkv, out, d_o, lse, cpb.tab2, cpb.alpha, dqkv, partial, cpb.dtab, cpb.dalpha, gq, gv, Bn, res, ws, shift,
+                   heads, hd)
+    got = pool.get(dqkv)
+    g_ref = leaves[0].grad
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        assert rel(got[:, sl], g_ref[:, sl]) < 1e-4, name
+    assert rel(gq, got[:, :C].sum(0)) < 1e-4 and rel(gv, got[:, 2 * C:].sum(0)) < 1e-4
+    cpb.backward()
+    assert rel(cpb.grad(2, w2.shape), leaves[3].grad) < 1e-3, "cpb w2 grad"
+    assert rel(cpb.grad(0, w1.shape), leaves[1].grad) < 1e-3, "cpb w1 grad"
+    assert rel(cpb.grad(3, (heads,)), leaves[4].grad.view(-1)) < 1e-3, "logit_scale grad"
+
+
+# ------------------------------------------------------------------------------------------------------
+# whole model
+# ------------------------------------------------------------------------------------------------------
+def build(name):
+    from poseidon_b200.scOT.model import ScOT, ScOTConfig
+
+    rec = torch.load(os.path.join(GOLD, f"{name}.pt"), weights_only=False)
+    cfg = ScOTConfig(**rec["config"])
+    w = make_weights(rec["shapes"], seed=0)
+    model = ScOT(cfg)
+    model.load_state_dict(w, strict=True)
+    model = model.cuda()
+    model.precision = "parity"
+    inputs = make_inputs(rec["batch"], cfg.num_channels, cfg.num_out_channels, cfg.image_size, seed=0,
+                         mask_channels=rec["mask_channels"])
+    return rec, cfg, w, model, inputs
+
+
+def engine_run(rec, cfg, model, inputs):
+    x, t, y, pm = inputs
+    return model(pixel_values=x.cuda(), time=t.cuda() if cfg.use_conditioning else None, labels=y.cuda(),
+                 pixel_mask=pm.cuda() if rec["mask_channels"] else None)
+
+
+@pytest.mark.parametrize("name", ["tiny_ln", "tiny", "T128", "B128"])
+def test_parity_mode_meets_north_star_tolerance(name):
+    """fixtures = outputs of the unmodified reference (oracle/make_golden.py): rel-L2 < 1e-3, loss rel < 1e-4"""
+    rec, cfg, w, model, inputs = build(name)
+    with torch.no_grad():
+        out = engine_run(rec, cfg, model, inputs)
+    r = rel(out.output.cpu(), rec["output"])
+    print(f"{name}: parity-mode output rel-L2 {r:.3e}, loss rel {abs(float(out.loss) - rec['loss']) / abs(rec['loss']):.3e}")
+    assert r < 1e-3
+    assert abs(float(out.loss) - rec["loss"]) < 1e-4 * abs(rec["loss"])
+    for c in rec["mask_channels"]:
+        assert torch.equal(out.output[:, c].cpu(), inputs[2][:, c])
+
+
+@pytest.mark.parametrize("name", ["tiny_ln", "tiny", "T128"])
+def test_parity_mode_gradients_every_parameter(name):
+    """smooth objective <G, prediction>; every parameter tensor individually within 1e-2, global rel-L2 < 2e-3"""
+    rec, cfg, w, model, inputs = build(name)
+    out = engine_run(rec, cfg, model, inputs)
+    G = torch.randn(out.output.shape, generator=torch.Generator().manual_seed(123))
+    out.output.backward(G.cuda())
+    x, t, y, pm = inputs
+    ocfg = types.SimpleNamespace(**rec["config"])
+    ocfg.learn_residual = False
+    if not hasattr(ocfg, "layer_norm_eps"):
+        ocfg.layer_norm_eps = 1e-5
+    wr = {k: v.double().requires_grad_(True) for k, v in w.items()}
+    loss, pred = O.scot_forward(ocfg, wr, x.double(), t.double() if ocfg.use_conditioning else None, y.double(),
+                                pm if rec["mask_channels"] else None)
+    (pred * G.double()).sum().backward()
+    grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+    num = sum((grads[k].double() - wr[k].grad).pow(2).sum() for k in grads)
+    den = sum(wr[k].grad.pow(2).sum() for k in grads)
+    g = float((num / den).sqrt())
+    errs = {k: rel(grads[k], wr[k].grad) for k in grads}
+    worst = max(errs, key=errs.get)
+    print(f"{name}: parity-mode gradient global rel-L2 {g:.3e}, worst tensor {worst} {errs[worst]:.3e}")
+    assert g < 2e-3
+    assert errs[worst] < 1e-2, (worst, errs[worst])
