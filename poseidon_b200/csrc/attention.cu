@@ -1123,6 +1123,12 @@ int scot_cpb_bwd_launch(const ScotCpbTable* tab, const float* params, float* gra
   return 0;
 }
 
+// SCOT_ATTN_TC=0: legacy mma.sync kernels for 16 x 16 windows as well (bring-up A/B)
+static bool attn_tc_enabled() {
+  const char* e = getenv("SCOT_ATTN_TC");
+  return !(e != nullptr && e[0] == '0');
+}
+
 #define ATTN_DISPATCH(WS_, HD_, CALL)                                                   \
   if (ws == WS_ && hd == HD_) { return CALL; }
 
@@ -1132,6 +1138,7 @@ int scot_attn_fwd_launch(const void* qkv, void* out, float* lse, const float* ta
   SCOT_REQUIRE(res % ws == 0 && (shift == 0 || shift == ws / 2), "attn_fwd: bad geometry res=%d ws=%d shift=%d", res, ws, shift);
   if (const size_t lo = scot_split_off())  // "parity" precision: fp32 attention on the split-bf16 tensors
     return scot_attn32_fwd_launch(qkv, out, lse, tab2, alpha, batch, res, ws, shift, heads, hd, lo, st);
+  if (ws == 16 && attn_tc_enabled()) return scot_attn_tc_fwd_launch(qkv, out, lse, tab2, alpha, batch, res, shift, heads, hd, st);
   WinGeom g{res, shift, res / ws, heads, heads * hd};
   const int tw = batch * g.nws * g.nws;
   ATTN_DISPATCH(16, 16, (launch_fwd<16, 16>(qkv, out, lse, tab2, alpha, g, tw, st)))
@@ -1163,6 +1170,11 @@ int scot_attn_bwd_launch2(const void* qkv, const void* o, const void* d_o, const
   if (const size_t lo = scot_split_off())
     return scot_attn32_bwd_launch(qkv, o, d_o, lse, tab2, alpha, dqkv, dtab, dalpha, g_qbias, g_vbias, batch, res, ws, shift,
                                   heads, hd, lo, st);
+  if (ws == 16 && attn_tc_enabled()) {
+    const int rc = scot_attn_tc_bwd_launch(qkv, o, d_o, lse, tab2, alpha, dqkv, dtab, dalpha, g_qbias, g_vbias, batch, res, shift,
+                                           heads, hd, st);
+    if (rc != -1) return rc;
+  }
   WinGeom g{res, shift, res / ws, heads, heads * hd};
   const int tw = batch * g.nws * g.nws;
 #define BWD_ARGS qkv, o, d_o, lse, tab2, alpha, dqkv, partial, partial_bytes, dtab, dalpha, g_qbias, g_vbias, g, tw, st, fk

@@ -33,6 +33,13 @@ int scot_attn_bwd_launch2(const void* qkv, const void* o, const void* d_o, const
                           const float* alpha, void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha,
                           float* g_qbias, float* g_vbias, int batch, int res, int ws, int shift, int heads, int hd,
                           cudaStream_t st, const ScotAttnBwdFork* fk);
+// attention_tc.cu: tcgen05 / TMEM / TMA kernels for 16 x 16 windows
+int scot_attn_tc_fwd_launch(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, int batch, int res,
+                            int shift, int heads, int hd, cudaStream_t st);
+// returns -1 when the shape is not covered (head_dim 64): the caller falls back to the mma.sync kernels
+int scot_attn_tc_bwd_launch(const void* qkv, const void* o, const void* d_o, const float* lse, const float* tab2,
+                            const float* alpha, void* dqkv, float* dtab, float* dalpha, float* g_qbias, float* g_vbias,
+                            int batch, int res, int shift, int heads, int hd, cudaStream_t st);
 // attention_f32.cu: fp32 CUDA-core attention of the "parity" precision mode (operands are hi + lo bf16 pairs, the lo
 // tensors `lo_off` bytes after the hi ones; lo_off = 0 reads / writes plain bf16)
 int scot_attn32_fwd_launch(const void* qkv, void* out, float* lse, const float* tab2, const float* alpha, int batch, int res,
