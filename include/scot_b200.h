@@ -131,6 +131,45 @@ int scot_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* 
                   void* dqkv, float* partial, size_t partial_bytes, float* dtab, float* dalpha, float* g_qbias,
                   float* g_vbias, int batch, int res, int ws, int shift, int heads, int head_dim, void* stream);
 
+/* ---- glue ops around the blocks (embedding, patch merging / unmerging, ConvNeXt skips, patch recovery, loss) ----------
+ * One entry point per kernel; the engine below calls the same launchers in ScOT.forward order. Index-only ops (im2col,
+ * merge gather / scatter, pixel unshuffle) are exact permutations (bit-exact tests in tests/test_gpu_glue.py). */
+/* out(bf16)[n] = in(f32)[n], n % 4 == 0 */
+int scot_cast_f32_bf16(const float* in, void* out, long n, void* stream);
+/* patch embedding as GEMM input (ScOTPatchEmbeddings, scOT/model.py:295-310): x [B,Cin,H,W] f32 ->
+ * out [B*(H/ps)*(W/ps), Cin*ps*ps] bf16, k = (c, di, dj); the projection itself is scot_gemm_bf16 */
+int scot_embed_im2col(const float* x, void* out, int B, int Cin, int H, int W, int ps, void* stream);
+/* ScOTPatchMerging gather (model.py:694-704, order (0,0),(1,0),(0,1),(1,1)): out [B*(res/2)^2, 4C] bf16 = x (+ inp) */
+int scot_merge_gather(const float* x, const float* inp, void* out, int B, int res, int C, void* stream);
+/* its backward: g_out [B*res^2, C] f32 = (g_in ? g_in : 0) + dG [B*(res/2)^2, 4C] scattered back */
+int scot_merge_scatter(const float* dG, const float* g_in, float* g_out, int B, int res, int C, void* stream);
+/* ConvNeXtBlock pieces (model.py:198-217): depthwise 7x7 (NHWC f32, pad 3) forward / backward, layer-scale residual.
+ * dwconv7_bwd: g_out = g_in + conv^T(dout), g_w += weight gradient. scale_add: out = in + gamma * z, zb = bf16(z);
+ * backward: dz(bf16) = gamma * g, g_gamma += sum g*z, g_bias += sum dz. */
+int scot_convnext_dwconv7_fwd(const float* x, const float* w, const float* bias, float* out, int B, int res, int C, void* stream);
+int scot_convnext_dwconv7_bwd(const float* x, const float* w, const float* dout, const float* g_in, float* g_out, float* g_w,
+                              int B, int res, int C, void* stream);
+int scot_convnext_scale_add_fwd(const float* in, const float* z, const float* gamma, float* out, void* zb, long rows, int C,
+                                void* stream);
+int scot_convnext_scale_add_bwd(const float* g, const void* zb, const float* gamma, void* dz, float* g_gamma, float* g_bias,
+                                long rows, int C, void* stream);
+/* ScOTPatchRecovery tail (model.py:639-647): D [tokens, OC*ps*ps] f32 (ConvTranspose2d as GEMM) -> planar P [B,OC,H,W];
+ * 5x5 mixing conv (+ learn_residual input, + pixel_mask overwrite: mask_mode 1 = [B,OC], 2 = [B,OC,H,W] uint8);
+ * backward: dP scratch (planar f32), dD [tokens, OC*ps*ps] bf16, g_w += mixup weight gradient, g_bias += projection bias */
+int scot_recovery_unshuffle(const float* D, float* P, int B, int OC, int H, int W, int ps, void* stream);
+int scot_recovery_conv5_fwd(const float* P, const float* w, const float* resid, int resid_channels, const float* labels,
+                            const uint8_t* mask, int mask_mode, float* pred, int B, int OC, int H, int W, void* stream);
+int scot_recovery_conv5_bwd(const float* P, const float* w, const float* dpred, float* dP_scratch, void* dD, float* g_w,
+                            float* g_bias, int B, int OC, int H, int W, int ps, void* stream);
+/* loss (model.py:1425-1484): p = 1 | 2; slices_host = channel_slice_list_normalized_loss (host array, n_slices entries)
+ * or NULL for the plain mean; sums = 20 floats of scratch (kept for backward). loss_bwd: dpred = gscale[0] * dloss/dpred
+ * (+ extra), zero where the mask overwrote the prediction. */
+int scot_loss_fwd(const float* pred, const float* labels, float* sums, float* loss, const int* slices_host, int n_slices, int p,
+                  int B, int OC, long HW, void* stream);
+int scot_loss_bwd(const float* pred, const float* labels, const float* sums, const float* gscale, const float* extra,
+                  const uint8_t* mask, int mask_mode, float* dpred, const int* slices_host, int n_slices, int p, int B, int OC,
+                  long HW, void* stream);
+
 /* ---- whole-model engine --------------------------------------------------------------------------
  * Mirrors ScOTConfig (scOT/model.py:66-132); replaces ScOT.forward (:1318-1509) + autograd backward. */
 typedef struct ScotModelDesc {

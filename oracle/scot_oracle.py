@@ -124,16 +124,16 @@ def window_attention(xw: Tensor, p: Dict[str, Tensor], pre: str, heads: int, ws:
     attn = F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)  # eps 1e-12
     scale = torch.clamp(p[sp + ".logit_scale"], max=math.log(1.0 / 0.01)).exp()
     attn = attn * scale
-    coords = relative_coords_table(ws).to(xw.dtype)
+    coords = relative_coords_table(ws).to(xw)  # same dtype AND device as the activations (the GPU eager baseline runs it on cuda)
     hid = F.relu(F.linear(coords, p[sp + ".continuous_position_bias_mlp.0.weight"],
                           p[sp + ".continuous_position_bias_mlp.0.bias"]))
     table = F.linear(hid, p[sp + ".continuous_position_bias_mlp.2.weight"])  # [(2ws-1)^2, heads]
-    idx = relative_position_index(ws).view(-1)
+    idx = relative_position_index(ws).view(-1).to(xw.device)
     bias = table[idx].view(n, n, heads).permute(2, 0, 1).contiguous()
     attn = attn + (16 * torch.sigmoid(bias)).unsqueeze(0)
     if mask is not None:
         nw = mask.shape[0]
-        m = mask.to(xw.dtype).unsqueeze(1).unsqueeze(0)
+        m = mask.to(xw).unsqueeze(1).unsqueeze(0)
         attn = attn.view(bw // nw, nw, heads, n, n) + m
         attn = attn + m  # HF 5.5.0 adds the mask twice (HF:465-468)
         attn = attn.view(-1, heads, n, n)

@@ -175,6 +175,25 @@ def _declare_engine(lib):
     lib.scot_adamw_step.restype = i
     lib.scot_lp_plane_sums.argtypes = [vp, vp, vp, i, l, l, vp]
     lib.scot_lp_plane_sums.restype = i
+    # glue ops
+    for name, args in (
+        ("scot_cast_f32_bf16", [vp, vp, l, vp]),
+        ("scot_embed_im2col", [vp, vp, i, i, i, i, i, vp]),
+        ("scot_merge_gather", [vp, vp, vp, i, i, i, vp]),
+        ("scot_merge_scatter", [vp, vp, vp, i, i, i, vp]),
+        ("scot_convnext_dwconv7_fwd", [vp, vp, vp, vp, i, i, i, vp]),
+        ("scot_convnext_dwconv7_bwd", [vp, vp, vp, vp, vp, vp, i, i, i, vp]),
+        ("scot_convnext_scale_add_fwd", [vp, vp, vp, vp, vp, l, i, vp]),
+        ("scot_convnext_scale_add_bwd", [vp, vp, vp, vp, vp, vp, l, i, vp]),
+        ("scot_recovery_unshuffle", [vp, vp, i, i, i, i, i, vp]),
+        ("scot_recovery_conv5_fwd", [vp, vp, vp, i, vp, vp, i, vp, i, i, i, i, vp]),
+        ("scot_recovery_conv5_bwd", [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp]),
+        ("scot_loss_fwd", [vp, vp, vp, vp, vp, i, i, i, i, l, vp]),
+        ("scot_loss_bwd", [vp, vp, vp, vp, vp, vp, i, vp, vp, i, i, i, i, l, vp]),
+    ):
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = i
 
 
 _declare_base = _declare
@@ -288,6 +307,15 @@ def attn_bwd(qkv, o, d_o, lse, tab2, alpha, dqkv, partial, dtab, dalpha, g_qbias
     check(load().scot_attn_bwd(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(tab2), ptr(alpha), ptr(dqkv), ptr(partial),
                                partial.numel() * partial.element_size(), ptr(dtab), ptr(dalpha), ptr(g_qbias),
                                ptr(g_vbias), batch, res, ws, shift, heads, hd, cur_stream()), "scot_attn_bwd")
+
+
+def glue(name, *args):
+    """Calls one of the glue entry points (scot_embed_im2col, scot_merge_gather, ... see scot_b200.h): tensors are passed
+    as torch CUDA tensors (or None), scalars as ints; the current stream is appended."""
+    import torch
+
+    conv = [ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a for a in args]
+    check(getattr(load(), name)(*conv, cur_stream()), name)
 
 
 class Engine:

@@ -103,12 +103,12 @@ __device__ __forceinline__ int quad_code(const TcGeom& g, int bw, int quad) {
 // L2-normalise one token row in place (F.normalize eps 1e-12, HF:445). The row occupies ROWB contiguous bytes; the swizzle
 // only permutes its 16-byte chunks, which a sum of squares / a uniform scale do not care about. Returns 1 / max(|x|, eps).
 template <int HD>
-__device__ __forceinline__ float normalize_row_inplace(uint8_t* row) {
+__device__ __forceinline__ float normalize_row_inplace(uint32_t row) {  // row = shared-space byte address
   uint4 u[HD / 8];
   float ss = 0.f;
 #pragma unroll
   for (int c = 0; c < HD / 8; ++c) {
-    u[c] = *reinterpret_cast<const uint4*>(row + 16 * c);
+    u[c] = lds128(row + 16 * c);
     const uint32_t w[4] = {u[c].x, u[c].y, u[c].z, u[c].w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -126,7 +126,7 @@ __device__ __forceinline__ float normalize_row_inplace(uint8_t* row) {
       const float2 f = unpack_bf16x2(w[k]);
       o[k] = pack_bf16x2(f.x * inv, f.y * inv);
     }
-    *reinterpret_cast<uint4*>(row + 16 * c) = make_uint4(o[0], o[1], o[2], o[3]);
+    sts128(row + 16 * c, o[0], o[1], o[2], o[3]);
   }
   return inv;
 }
@@ -156,16 +156,42 @@ template <int HD>
 struct FwdSmem {
   using Cfg = TcCfg<HD>;
   static constexpr int kBar = 0;                        // 2 mbarriers + tmem pointer
-  static constexpr int kTab = 64;                       // 31 x 40 floats
-  static constexpr int kQ = 5120;                       // 1024-aligned from here on
+  static constexpr int kQ = 1024;                       // 1024-aligned from here on
   static constexpr int kK = kQ + 2 * Cfg::QUADB;
   static constexpr int kV = kK + Cfg::TILEB;
   static constexpr int kP = kV + Cfg::TILEB;            // 4 slabs x [128 rows x 128 B]
   static constexpr int kTotal = kP + 4 * 16384;
 };
 
+// 32 lanes x 32 columns of 32-bit, registers -> TMEM (inverse of tmem_ld_32x32)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
+// One CTA = 256 threads = one query half (128 rows x 256 keys) of one (window, head); warp = (TMEM lane quarter, column
+// half). Pass 1 adds bias + mask, takes the row maximum and parks the biased scores back in TMEM (tcgen05.st); pass 2
+// exponentiates, sums and stages P. The two warps of a row exchange maximum / sum through the (then dead) q tile.
 template <int HD>
-__global__ void __launch_bounds__(128, (FwdSmem<HD>::kTotal + 1024 <= 113 * 1024) ? 2 : 1)
+__global__ void __launch_bounds__(256, (FwdSmem<HD>::kTotal + 1024 + 5120 <= 113 * 1024) ? 2 : 1)
 attn_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
   using Cfg = TcCfg<HD>;
   using SM = FwdSmem<HD>;
@@ -174,13 +200,16 @@ attn_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
   uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem + SM::kBar);
   uint64_t* bar_mma = bar_tma + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_tma + 2);
-  float* stab = reinterpret_cast<float*>(smem + SM::kTab);
+  __shared__ float stab[31 * kTabPitch];  // static: the compiler knows the address space (LDS with immediate offsets)
   uint8_t* sQ = smem + SM::kQ;
   uint8_t* sK = smem + SM::kK;
   uint8_t* sV = smem + SM::kV;
   uint8_t* sP = smem + SM::kP;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lq = warp & 3, ch = warp >> 2;
+  const int row = lq * 32 + lane;  // accumulator row (query within this half)
   const TcGeom g = a.g;
+  const uint32_t xch = smem_u32(sQ);  // exchange area [2][2][128] floats: max, sum per (column half, row)
 
   pdl_launch_dependents();
   if (tid == 0) {
@@ -214,15 +243,14 @@ attn_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
       }
     }
     if (h != cur_head) {
-      for (int i = tid; i < kTabN; i += 128) stab[(i / 31) * kTabPitch + (i % 31)] = a.tab2[i * g.heads + h];
+      for (int i = tid; i < kTabN; i += 256) stab[(i / 31) * kTabPitch + (i % 31)] = a.tab2[i * g.heads + h];
       cur_head = h;
     }
     mbar_wait(bar_tma, ph_tma);
     ph_tma ^= 1u;
-    // ---- cosine attention: normalise q (my row) and k (two rows) in place ----
-    normalize_row_inplace<HD>(sQ + tid * Cfg::ROWB);
-    normalize_row_inplace<HD>(sK + tid * Cfg::ROWB);
-    normalize_row_inplace<HD>(sK + (tid + 128) * Cfg::ROWB);
+    // ---- cosine attention: normalise q (128 rows) and k (256 rows) in place ----
+    if (tid < 128) normalize_row_inplace<HD>(smem_u32(sQ) + tid * Cfg::ROWB);
+    normalize_row_inplace<HD>(smem_u32(sK) + tid * Cfg::ROWB);
     fence_proxy_async_smem();
     __syncthreads();
     // ---- S[128 x 256] = q_hat k_hat^T ----
@@ -238,45 +266,51 @@ attn_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
       umma_commit(bar_mma);
     }
     // per-row constants while the MMA runs
-    const int m = half * 128 + tid;  // tile row of this thread
+    const int m = half * 128 + row;  // tile row of this thread
     int pm, qm;
     row_pq(m, pm, qm);
     const float a2 = a.alpha[h] * kLog2e;
     const float* tb = stab + (pm * kTabPitch + qm + 15 * kTabPitch + 15);
     const int code_m = quad_code(g, bw, m >> 6);
-    float mterm[4];
-#pragma unroll
-    for (int quad = 0; quad < 4; ++quad) mterm[quad] = (quad_code(g, bw, quad) != code_m) ? -200.0f * kLog2e : 0.f;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // this thread's columns: quadrants 2 ch and 2 ch + 1
+    const float mt0 = (quad_code(g, bw, 2 * ch) != code_m) ? -200.0f * kLog2e : 0.f;
+    const float mt1 = (quad_code(g, bw, 2 * ch + 1) != code_m) ? -200.0f * kLog2e : 0.f;
+    const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * 128);
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1u;
     tc_fence_after();
-    // ---- pass 1: row maximum of S * alpha + bias + mask (log2 units) ----
+    // ---- pass 1: biased scores (log2 units) back to TMEM, row maximum ----
     float mx = -INFINITY;
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
+    for (int cc = 0; cc < 4; ++cc) {
       float s[32];
       tmem_ld_32x32(trow + cc * 32, s);
       tmem_ld_wait();
-      const float* tk = tb - chunk_off(cc);
-      const float mt = mterm[cc >> 1];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(s[j], a2, tk[-col_imm(j)]) + mt);
-    }
-    // ---- pass 2: P = exp2(. - max) as bf16 into the staging tile, row sum ----
-    float l = 0.f;
-    const uint32_t prow = smem_u32(sP) + (uint32_t)tid * 128u;
-    const uint32_t swz = (uint32_t)(tid & 7);
-#pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      float s[32];
-      tmem_ld_32x32(trow + cc * 32, s);
-      tmem_ld_wait();
-      const float* tk = tb - chunk_off(cc);
-      const float mt = mterm[cc >> 1] - mx;
+      const float* tk = tb - ((((ch << 3) + ((cc & 1) << 2)) * kTabPitch) + ((cc >> 1) << 3));
+      const float mt = (cc >> 1) ? mt1 : mt0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        s[j] = fast_exp2(fmaf(s[j], a2, tk[-col_imm(j)]) + mt);
+        s[j] = fmaf(s[j], a2, tk[-col_imm(j)]) + mt;
+        mx = fmaxf(mx, s[j]);
+      }
+      tmem_st_32x32(trow + cc * 32, s);
+    }
+    sts_f32(xch + (uint32_t)(ch * 128 + row) * 4u, mx);
+    tmem_st_wait();
+    __syncthreads();  // q tile is dead (S is complete): its first 2 KB serve as the exchange area
+    mx = fmaxf(mx, lds_f32(xch + (uint32_t)((ch ^ 1) * 128 + row) * 4u));
+    // ---- pass 2: P = exp2(. - max) as bf16 into the staging tile, row sum ----
+    float l = 0.f;
+    const uint32_t prow = smem_u32(sP) + (uint32_t)row * 128u + (uint32_t)ch * 32768u;
+    const uint32_t swz = (uint32_t)(row & 7);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      float s[32];
+      tmem_ld_32x32(trow + cc * 32, s);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        s[j] = fast_exp2(s[j] - mx);
         l += s[j];
       }
       const uint32_t slab = prow + (uint32_t)(cc >> 1) * 16384u;
@@ -287,10 +321,11 @@ attn_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
                pack_bf16x2(s[8 * c4 + 4], s[8 * c4 + 5]), pack_bf16x2(s[8 * c4 + 6], s[8 * c4 + 7]));
       }
     }
+    sts_f32(xch + 1024u + (uint32_t)(ch * 128 + row) * 4u, l);
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
-    // ---- O[128 x HD] = P v (accumulator reuses the first HD columns of the dead S tile) ----
+    // ---- O[128 x HD] = P v (accumulator reuses the first HD columns of the dead score tile) ----
     if (tid == 0) {
       tc_fence_after();
       constexpr uint32_t idesc = umma_idesc_bf16(128, HD, 0, 1);
@@ -303,26 +338,28 @@ attn_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
       umma_commit(bar_mma);
     }
     const long tr = token_of(g, bw, pm, qm);
+    l += lds_f32(xch + 1024u + (uint32_t)((ch ^ 1) * 128 + row) * 4u);
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1u;
     tc_fence_after();
     {
-      const float il = 1.0f / l;
-      bf16* dst = a.out + tr * g.C + h * HD;
-#pragma unroll
-      for (int c0 = 0; c0 < HD; c0 += 32) {
-        constexpr int W = HD < 32 ? HD : 32;
+      // the two warps of a row split the HD output columns (head_dim 16: the first one takes them all)
+      constexpr int W = HD >= 32 ? HD / 2 : HD;
+      if (HD >= 32 || ch == 0) {
+        const float il = 1.0f / l;
+        const int c0 = HD >= 32 ? ch * W : 0;
+        bf16* dst = a.out + tr * g.C + h * HD + c0;
         float o[32];
-        if constexpr (W == 32) tmem_ld_32x32(trow + c0, o);
-        else tmem_ld_32x16(trow + c0, o);
+        if constexpr (W == 32) tmem_ld_32x32(tmem_base + ((uint32_t)(lq * 32) << 16) + c0, o);
+        else tmem_ld_32x16(tmem_base + ((uint32_t)(lq * 32) << 16) + c0, o);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < W; c += 8)
-          *reinterpret_cast<uint4*>(dst + c0 + c) =
+          *reinterpret_cast<uint4*>(dst + c) =
               make_uint4(pack_bf16x2(o[c] * il, o[c + 1] * il), pack_bf16x2(o[c + 2] * il, o[c + 3] * il),
                          pack_bf16x2(o[c + 4] * il, o[c + 5] * il), pack_bf16x2(o[c + 6] * il, o[c + 7] * il));
+        if (ch == 0) a.lse[(long)unit * kN + pm * 16 + qm] = mx + log2f(l);
       }
-      a.lse[(long)unit * kN + pm * 16 + qm] = mx + log2f(l);
     }
     tc_fence_before();
     __syncthreads();  // TMEM and the operand tiles are free for the next item
@@ -332,7 +369,6 @@ attn_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
     tmem_dealloc<256>(tmem_base);
   }
 }
-
 
 // =================================================================================================
 // backward. One CTA = 512 threads = one (window, head) at a time, persistent over units.
@@ -355,8 +391,7 @@ attn_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
 struct TcBwdArgs {
   CUtensorMap tm_qkv;  // [B, res, res, 3C] bf16, box {HD, 8, 8, 1}
   CUtensorMap tm_do;   // [B, res, res, C]
-  const bf16* o;       // [tokens, C]
-  const bf16* d_o;     // [tokens, C]
+  CUtensorMap tm_o;    // [B, res, res, C]
   const float* lse;    // [units, 256]
   const float* tab2;
   const float* alpha;
@@ -373,17 +408,15 @@ template <int HD>
 struct BwdSmem {
   using Cfg = TcCfg<HD>;
   static constexpr int kBar = 0;                       // 3 mbarriers + tmem pointer
-  static constexpr int kTab = 64;                      // 31 x 40 floats
-  static constexpr int kRow = 5120;                    // inv_q, inv_k, lse, delta: 4 x 256 floats
-  static constexpr int kCol = kRow + 4096;             // column sums dq[HD], dv[HD], dalpha: 2*HD + 1 floats
-  static constexpr int kW = kCol + 1024;               // 31 x 16 x 16 floats
-  static constexpr int kQ = ((kW + 31 * 256 * 4) + 1023) / 1024 * 1024;
+  static constexpr int kQ = 1024;
   static constexpr int kK = kQ + Cfg::TILEB;
   static constexpr int kV = kK + Cfg::TILEB;
   static constexpr int kDO = kV + Cfg::TILEB;
-  static constexpr int kP = kDO + Cfg::TILEB;          // [2 slabs][128 rows][128 B]
-  static constexpr int kDS = kP + 32768;
-  static constexpr int kTotal = kDS + 32768;
+  static constexpr int kO = kDO + Cfg::TILEB;          // forward output (only for delta = rowsum(dO * O))
+  static constexpr int kP = kO + Cfg::TILEB;           // [2 slabs][128 rows][128 B]
+  static constexpr int kDS = kP + 32768;               // two buffers (alternate by step) of the same shape
+  static constexpr int kTotal = kDS + 2 * 32768;
+  static constexpr int kStatic = (31 * kTabPitch + 4 * 256 + 2 * HD + 1 + 31 * 256) * 4;  // table, row arrays, sums, W
 };
 
 // 16-byte chunk c of tile row r sits at physical chunk c ^ swz_of(r) (Swizzle<B,4,3> on the byte address)
@@ -393,12 +426,12 @@ __device__ __forceinline__ uint32_t swz_of(int r) {
   return (uint32_t)(((r * ROWB) >> 7) & (ROWB / 16 - 1));
 }
 template <int HD>
-__device__ __forceinline__ void load_row_deswizzled(float* v, const uint8_t* tile, int r) {
+__device__ __forceinline__ void load_row_deswizzled(float* v, uint32_t tile, int r) {  // tile = shared-space address
   constexpr int ROWB = HD * 2;
   const uint32_t sw = swz_of<HD>(r);
 #pragma unroll
   for (int c = 0; c < HD / 8; ++c) {
-    const uint4 u = *reinterpret_cast<const uint4*>(tile + (size_t)r * ROWB + (((uint32_t)c ^ sw) << 4));
+    const uint4 u = lds128(tile + (uint32_t)r * ROWB + (((uint32_t)c ^ sw) << 4));
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -406,6 +439,41 @@ __device__ __forceinline__ void load_row_deswizzled(float* v, const uint8_t* til
       v[8 * c + 2 * k] = f.x;
       v[8 * c + 2 * k + 1] = f.y;
     }
+  }
+}
+
+// Bias-gradient fold of one staged 128 x 128 dS tile (see the kernel header). Thread = (hc, j_m, b_m | G8, b_n): it sums, over
+// the 8 window rows i_m of the tile, the four dS values of key pixels (i_n = (i_m - G8) mod 8, j_n = 4 hc .. 4 hc + 3) of
+// key quadrant column b_n -> row displacement G8 (i_m >= G8) or G8 - 8 (i_m < G8); lanes of a warp read 32 distinct banks.
+template <int G8>
+__device__ __forceinline__ void fold_ds(uint32_t sds, float* sW, int lane, int b_n, int dquad /* h - kb */) {
+  const int hc = lane & 1, j_m = (lane >> 1) & 7, b_m = lane >> 4;
+  float acc_hi[4] = {0.f, 0.f, 0.f, 0.f}, acc_lo[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t base = sds + (uint32_t)(b_n * 16384 + (64 * b_m + j_m) * 128 + hc * 8);
+#pragma unroll
+  for (int i_m = 0; i_m < 8; ++i_m) {
+    const int i_n = (i_m - G8) & 7;
+    uint2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y)
+                 : "r"(base + (uint32_t)(i_m * 8 * 128) + (uint32_t)((i_n ^ j_m) << 4)));
+    const float2 f01 = unpack_bf16x2(v.x), f23 = unpack_bf16x2(v.y);
+    if (i_m >= G8) {
+      acc_hi[0] += f01.x; acc_hi[1] += f01.y; acc_hi[2] += f23.x; acc_hi[3] += f23.y;
+    } else {
+      acc_lo[0] += f01.x; acc_lo[1] += f01.y; acc_lo[2] += f23.x; acc_lo[3] += f23.y;
+    }
+  }
+  const int qmm = 8 * b_m + j_m, qn0 = 8 * b_n + 4 * hc;
+  const int dpi = 8 * dquad + G8 + 15;  // table row of displacement pm - pn = 8 (h - kb) + G8
+  float4* w_hi = reinterpret_cast<float4*>(sW + dpi * 256 + qmm * 16 + qn0);
+  float4 t = *w_hi;
+  t.x += acc_hi[0]; t.y += acc_hi[1]; t.z += acc_hi[2]; t.w += acc_hi[3];
+  *w_hi = t;
+  if (G8 > 0) {
+    float4* w_lo = reinterpret_cast<float4*>(sW + (dpi - 8) * 256 + qmm * 16 + qn0);
+    float4 t2 = *w_lo;
+    t2.x += acc_lo[0]; t2.y += acc_lo[1]; t2.z += acc_lo[2]; t2.w += acc_lo[3];
+    *w_lo = t2;
   }
 }
 
@@ -417,23 +485,23 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
   constexpr int kTmemS = 0, kTmemDP = 128, kTmemDQ = 256, kTmemDK = 256 + 2 * HD, kTmemDV = 256 + 4 * HD;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem + SM::kBar);
+  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem + SM::kBar);  // q, k tiles have landed
   uint64_t* bar_s = bar_tma + 1;   // S / dP of the current step are in TMEM
   uint64_t* bar_o = bar_tma + 2;   // the dQ / dK / dV MMAs of the previous step have read the staging tiles
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_tma + 3);
-  float* stab = reinterpret_cast<float*>(smem + SM::kTab);
-  float* s_invq = reinterpret_cast<float*>(smem + SM::kRow);
-  float* s_invk = s_invq + 256;
-  float* s_lse = s_invk + 256;
-  float* s_delta = s_lse + 256;
-  float* s_col = reinterpret_cast<float*>(smem + SM::kCol);  // [0,HD) dq sums, [HD,2HD) dv sums, [2HD] dalpha
-  float* sW = reinterpret_cast<float*>(smem + SM::kW);
+  uint64_t* bar_tma2 = bar_tma + 3;  // v, dO, O tiles have landed (prefetched under the previous unit's epilogue)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_tma + 4);
+  // small hot arrays are static: the compiler then knows their address space (LDS / STS, immediate offsets)
+  __shared__ float stab[31 * kTabPitch];
+  __shared__ float s_invq[256], s_invk[256], s_lse[256], s_delta[256];
+  __shared__ float s_col[2 * HD + 1];  // [0,HD) dq sums, [HD,2HD) dv sums, [2HD] dalpha
+  __shared__ __align__(16) float sW[31 * 256];
   uint8_t* sQ = smem + SM::kQ;
   uint8_t* sK = smem + SM::kK;
   uint8_t* sV = smem + SM::kV;
   uint8_t* sDO = smem + SM::kDO;
+  uint8_t* sO = smem + SM::kO;
   uint8_t* sP = smem + SM::kP;
-  uint8_t* sDS = smem + SM::kDS;
+  uint8_t* sDS0 = smem + SM::kDS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lq = warp & 3, cg = warp >> 2;           // TMEM lane quarter, 32-column group of the 128-wide tile
   const int m_local = lq * 32 + lane;                // accumulator row of this thread
@@ -443,9 +511,11 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
   if (tid == 0) {
     tma_prefetch_desc(&a.tm_qkv);
     tma_prefetch_desc(&a.tm_do);
+    tma_prefetch_desc(&a.tm_o);
     mbar_init(bar_tma, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
+    mbar_init(bar_tma2, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_ptr_smem);
@@ -479,6 +549,28 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
     __syncthreads();
   };
 
+  auto load_qk = [&](int bw, int h) {  // one thread
+    mbar_expect_tx(bar_tma, 2 * Cfg::TILEB);
+#pragma unroll
+    for (int quad = 0; quad < 4; ++quad) {
+      int j0, i0, b;
+      quad_origin(g, bw, quad >> 1, quad & 1, j0, i0, b);
+      tma_load_4d(sQ + quad * Cfg::QUADB, &a.tm_qkv, bar_tma, h * HD, j0, i0, b);
+      tma_load_4d(sK + quad * Cfg::QUADB, &a.tm_qkv, bar_tma, g.C + h * HD, j0, i0, b);
+    }
+  };
+  auto load_vdo = [&](int bw, int h) {  // one thread
+    mbar_expect_tx(bar_tma2, 3 * Cfg::TILEB);
+#pragma unroll
+    for (int quad = 0; quad < 4; ++quad) {
+      int j0, i0, b;
+      quad_origin(g, bw, quad >> 1, quad & 1, j0, i0, b);
+      tma_load_4d(sV + quad * Cfg::QUADB, &a.tm_qkv, bar_tma2, 2 * g.C + h * HD, j0, i0, b);
+      tma_load_4d(sDO + quad * Cfg::QUADB, &a.tm_do, bar_tma2, h * HD, j0, i0, b);
+      tma_load_4d(sO + quad * Cfg::QUADB, &a.tm_o, bar_tma2, h * HD, j0, i0, b);
+    }
+  };
+
   uint32_t ph_tma = 0, ph_s = 0, ph_o = 0;
   int cur_head = -1;
   // head-major unit order, strided over the CTAs: a CTA changes head at most (heads - 1) times
@@ -490,30 +582,24 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
       for (int i = tid; i < kTabN; i += 512) stab[(i / 31) * kTabPitch + (i % 31)] = a.tab2[i * g.heads + h];
       cur_head = h;
     }
-    // ---- loads ----
-    if (tid == 0) {
-      mbar_expect_tx(bar_tma, 4 * Cfg::TILEB);
-#pragma unroll
-      for (int quad = 0; quad < 4; ++quad) {
-        int j0, i0, b;
-        quad_origin(g, bw, quad >> 1, quad & 1, j0, i0, b);
-        tma_load_4d(sQ + quad * Cfg::QUADB, &a.tm_qkv, bar_tma, h * HD, j0, i0, b);
-        tma_load_4d(sK + quad * Cfg::QUADB, &a.tm_qkv, bar_tma, g.C + h * HD, j0, i0, b);
-        tma_load_4d(sV + quad * Cfg::QUADB, &a.tm_qkv, bar_tma, 2 * g.C + h * HD, j0, i0, b);
-        tma_load_4d(sDO + quad * Cfg::QUADB, &a.tm_do, bar_tma, h * HD, j0, i0, b);
-      }
+    // ---- loads: (v, dO, O) were prefetched under the previous unit's epilogue, (q, k) right after it ----
+    if (u == (int)blockIdx.x && tid == 0) {
+      load_vdo(bw, h);
+      load_qk(bw, h);
     }
-    // delta_r = dO_r . O_r and the saved log-sum-exp of tile row r (threads 0..255), straight from global memory
     if (tid < 256) {
       int p, q;
       row_pq(tid, p, q);
-      const long tr = token_of(g, bw, p, q);
-      const uint4* po = reinterpret_cast<const uint4*>(a.o + tr * g.C + h * HD);
-      const uint4* pd = reinterpret_cast<const uint4*>(a.d_o + tr * g.C + h * HD);
+      s_lse[tid] = a.lse[(long)unit * kN + p * 16 + q];
+    }
+    mbar_wait(bar_tma2, ph_tma);
+    // delta_r = dO_r . O_r: both tiles carry the same swizzle, so chunk c of one row pairs with chunk c of the other
+    if (tid >= 256) {
+      const int r = tid - 256;
       float d = 0.f;
 #pragma unroll
       for (int c = 0; c < HD / 8; ++c) {
-        const uint4 x = po[c], y = pd[c];
+        const uint4 x = lds128(smem_u32(sO) + r * Cfg::ROWB + 16 * c), y = lds128(smem_u32(sDO) + r * Cfg::ROWB + 16 * c);
         const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -521,13 +607,12 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
           d = fmaf(f.x, e.x, fmaf(f.y, e.y, d));
         }
       }
-      s_delta[tid] = d;
-      s_lse[tid] = a.lse[(long)unit * kN + p * 16 + q];
+      s_delta[r] = d;
     }
     mbar_wait(bar_tma, ph_tma);
     ph_tma ^= 1u;
-    if (tid < 256) s_invq[tid] = normalize_row_inplace<HD>(sQ + tid * Cfg::ROWB);
-    else s_invk[tid - 256] = normalize_row_inplace<HD>(sK + (tid - 256) * Cfg::ROWB);
+    if (tid < 256) s_invq[tid] = normalize_row_inplace<HD>(smem_u32(sQ) + tid * Cfg::ROWB);
+    else s_invk[tid - 256] = normalize_row_inplace<HD>(smem_u32(sK) + (tid - 256) * Cfg::ROWB);
     fence_proxy_async_smem();
     __syncthreads();
 
@@ -550,6 +635,7 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
 #pragma unroll 1
     for (int step = 0; step < 4; ++step) {
       const int hh = step >> 1, kb = step & 1;
+      uint8_t* sDS = sDS0 + (step & 1) * 32768;  // alternating buffers: the fold of step s reads while step s+1 writes
       // per-row / per-column-group constants of this step
       const int m = hh * 128 + m_local;
       int pm, qm;
@@ -634,53 +720,35 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
         umma_commit(bar_o);
       }
       // ---- bias-gradient fold of the staged dS tile (generic-proxy reads, concurrent with the MMAs) ----
-      {
-        // thread = (hc, j_m, b_m | g8, b_n): lanes of a warp read 32 distinct banks
-        const int hc = lane & 1, j_m = (lane >> 1) & 7, b_m = lane >> 4;
-        const int g8 = warp & 7, b_n = warp >> 3;
-        float acc_hi[4] = {0.f, 0.f, 0.f, 0.f}, acc_lo[4] = {0.f, 0.f, 0.f, 0.f};  // row displacement g8 / g8 - 8
-#pragma unroll
-        for (int i_m = 0; i_m < 8; ++i_m) {
-          const int i_n = (i_m - g8) & 7;
-          const int r = 64 * b_m + 8 * i_m + j_m;
-          const uint2 v = *reinterpret_cast<const uint2*>(sDS + b_n * 16384 + r * 128 + ((i_n ^ j_m) << 4) + hc * 8);
-          const float2 f01 = unpack_bf16x2(v.x), f23 = unpack_bf16x2(v.y);
-          if (i_m >= g8) {
-            acc_hi[0] += f01.x; acc_hi[1] += f01.y; acc_hi[2] += f23.x; acc_hi[3] += f23.y;
-          } else {
-            acc_lo[0] += f01.x; acc_lo[1] += f01.y; acc_lo[2] += f23.x; acc_lo[3] += f23.y;
-          }
-        }
-        const int qmm = 8 * b_m + j_m, qn0 = 8 * b_n + 4 * hc;
-        const int dpi = 8 * (hh - kb) + g8 + 15;  // table row of displacement pm - pn = 8 (h - kb) + g8
-        float4* w_hi = reinterpret_cast<float4*>(sW + dpi * 256 + qmm * 16 + qn0);
-        float4 t = *w_hi;
-        t.x += acc_hi[0]; t.y += acc_hi[1]; t.z += acc_hi[2]; t.w += acc_hi[3];
-        *w_hi = t;
-        if (g8 > 0) {
-          float4* w_lo = reinterpret_cast<float4*>(sW + (dpi - 8) * 256 + qmm * 16 + qn0);
-          float4 t2 = *w_lo;
-          t2.x += acc_lo[0]; t2.y += acc_lo[1]; t2.z += acc_lo[2]; t2.w += acc_lo[3];
-          *w_lo = t2;
-        }
+      switch (warp & 7) {
+        case 0: fold_ds<0>(smem_u32(sDS), sW, lane, warp >> 3, hh - kb); break;
+        case 1: fold_ds<1>(smem_u32(sDS), sW, lane, warp >> 3, hh - kb); break;
+        case 2: fold_ds<2>(smem_u32(sDS), sW, lane, warp >> 3, hh - kb); break;
+        case 3: fold_ds<3>(smem_u32(sDS), sW, lane, warp >> 3, hh - kb); break;
+        case 4: fold_ds<4>(smem_u32(sDS), sW, lane, warp >> 3, hh - kb); break;
+        case 5: fold_ds<5>(smem_u32(sDS), sW, lane, warp >> 3, hh - kb); break;
+        case 6: fold_ds<6>(smem_u32(sDS), sW, lane, warp >> 3, hh - kb); break;
+        default: fold_ds<7>(smem_u32(sDS), sW, lane, warp >> 3, hh - kb); break;
       }
-      __syncthreads();  // every thread is done reading the staged dS tile before the next step overwrites it
     }
     // ---- epilogue: all products of this unit are complete when the last output commit arrives ----
     mbar_wait(bar_o, ph_o);
     ph_o ^= 1u;
     tc_fence_after();
+    const int u_next = u + (int)gridDim.x;
+    // every MMA of this unit is complete: v, dO (and O) are dead -> fetch the next unit's under the epilogue
+    if (tid == 0 && u_next < a.units) load_vdo(u_next % a.nwin, u_next / a.nwin);
+    // warps 0-7: dQ (normalisation backward + bias column sums); warps 8-15: dK (normalisation backward), then dV (sums)
 #pragma unroll 1
-    for (int task = warp; task < 24; task += 16) {
-      const int blk = task >> 2;                 // 0,1: dQ halves; 2,3: dK halves; 4,5: dV halves
+    for (int pass = 0; pass < (warp < 8 ? 1 : 2); ++pass) {
+      const int blk = warp < 8 ? (warp >> 2) : (pass == 0 ? 2 + ((warp - 8) >> 2) : 4 + ((warp - 8) >> 2));
       const int r = (blk & 1) * 128 + lq * 32 + lane;  // tile row (query or key)
       const uint32_t tcol = (blk < 2 ? kTmemDQ : (blk < 4 ? kTmemDK : kTmemDV)) + (uint32_t)((blk & 1) * HD);
-      float acc[HD];
+      float acc[32];  // HD <= 32 columns of this row (zero padded: the column-sum butterfly works on 32)
 #pragma unroll
-      for (int c0 = 0; c0 < HD; c0 += 32) {
-        if constexpr (HD >= 32) tmem_ld_32x32(tmem_base + ((uint32_t)(lq * 32) << 16) + tcol + c0, acc + c0);
-        else tmem_ld_32x16(tmem_base + ((uint32_t)(lq * 32) << 16) + tcol + c0, acc + c0);
-      }
+      for (int c = HD; c < 32; ++c) acc[c] = 0.f;
+      if constexpr (HD >= 32) tmem_ld_32x32(tmem_base + ((uint32_t)(lq * 32) << 16) + tcol, acc);
+      else tmem_ld_32x16(tmem_base + ((uint32_t)(lq * 32) << 16) + tcol, acc);
       tmem_ld_wait();
       int p, q;
       row_pq(r, p, q);
@@ -689,7 +757,7 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
       if (blk < 4) {
         // through the normalisation: d x = (alpha acc - x_hat (x_hat . alpha acc)) / max(|x|, eps)
         float xh[HD];
-        load_row_deswizzled<HD>(xh, blk < 2 ? sQ : sK, r);
+        load_row_deswizzled<HD>(xh, smem_u32(blk < 2 ? sQ : sK), r);
         float proj = 0.f;
 #pragma unroll
         for (int c = 0; c < HD; ++c) proj = fmaf(xh[c], acc[c], proj);
@@ -701,26 +769,37 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
           if (lane == 0) atomicAdd(&s_col[2 * HD], dal);
         }
       }
+      uint32_t pk[16];
+#pragma unroll
+      for (int c = 0; c < HD; c += 2) pk[c >> 1] = pack_bf16x2(acc[c], acc[c + 1]);
 #pragma unroll
       for (int c = 0; c < HD; c += 8)
-        *reinterpret_cast<uint4*>(dst + c) = make_uint4(pack_bf16x2(acc[c], acc[c + 1]), pack_bf16x2(acc[c + 2], acc[c + 3]),
-                                                        pack_bf16x2(acc[c + 4], acc[c + 5]), pack_bf16x2(acc[c + 6], acc[c + 7]));
+        *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[c >> 1], pk[(c >> 1) + 1], pk[(c >> 1) + 2], pk[(c >> 1) + 3]);
       if (blk < 2 || blk >= 4) {
-        // bias gradients: column sums of dq / dv (as stored)
-        float mine = 0.f;
+        // bias gradients = column sums of dq / dv as stored. Butterfly: after the step with lane distance d every lane keeps
+        // the half of its columns selected by bit d of its index -> 31 shuffles, lane L ends with the sum of column L.
 #pragma unroll
-        for (int c = 0; c < HD; ++c) {
-          const float v = warp_sum(bf16_round(acc[c]));
-          if ((c & 31) == lane) mine = v;
-          if ((c & 31) == 31 || c == HD - 1) {
-            const int col = (c & ~31) + lane;
-            if (col < HD) atomicAdd(&s_col[(blk >= 4 ? HD : 0) + col], mine);
+        for (int c = 0; c < HD; c += 2) {
+          const float2 f = unpack_bf16x2(pk[c >> 1]);
+          acc[c] = f.x;
+          acc[c + 1] = f.y;
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+          const bool up = (lane & d) != 0;
+#pragma unroll
+          for (int i = 0; i < d; ++i) {
+            const float keep = up ? acc[i + d] : acc[i];
+            const float send = up ? acc[i] : acc[i + d];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
           }
         }
+        if (lane < HD) atomicAdd(&s_col[(blk >= 4 ? HD : 0) + lane], acc[0]);
       }
     }
     tc_fence_before();
-    __syncthreads();  // accumulators, operand tiles and row arrays are free for the next unit
+    __syncthreads();  // accumulators, q / k tiles and row arrays are free for the next unit
+    if (tid == 0 && u_next < a.units) load_qk(u_next % a.nwin, u_next / a.nwin);
   }
   if (cur_head >= 0) flush_head(cur_head);
   if (warp == 0) {
@@ -786,7 +865,7 @@ int launch_tc_fwd(const void* qkv, void* out, float* lse, const float* tab2, con
   a.g = g;
   a.items = batch * g.nws * g.nws * g.heads * 2;
   constexpr int smem = SM::kTotal + 1024;
-  constexpr int per_sm = smem <= 113 * 1024 ? 2 : 1;
+  constexpr int per_sm = smem + 5120 <= 113 * 1024 ? 2 : 1;  // + the static bias table
   static bool done = false;
   if (!done) {
     SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -794,7 +873,7 @@ int launch_tc_fwd(const void* qkv, void* out, float* lse, const float* tab2, con
   }
   int grid = num_sms_tc() * per_sm;
   if (grid > a.items) grid = a.items;
-  SCOT_CHECK_CUDA(scot_launch_pdl(attn_tc_fwd_kernel<HD>, dim3(grid), dim3(128), (size_t)smem, st, a));
+  SCOT_CHECK_CUDA(scot_launch_pdl(attn_tc_fwd_kernel<HD>, dim3(grid), dim3(256), (size_t)smem, st, a));
   SCOT_LAUNCH_CHECK();
   return 0;
 }
@@ -812,8 +891,8 @@ int launch_tc_bwd(const void* qkv, const void* o, const void* d_o, const float* 
   if (rc) return rc;
   rc = make_tmap_tokens(&a.tm_do, d_o, batch, g.res, g.C, HD);
   if (rc) return rc;
-  a.o = (const bf16*)o;
-  a.d_o = (const bf16*)d_o;
+  rc = make_tmap_tokens(&a.tm_o, o, batch, g.res, g.C, HD);
+  if (rc) return rc;
   a.lse = lse;
   a.tab2 = tab2;
   a.alpha = alpha;
@@ -826,7 +905,7 @@ int launch_tc_bwd(const void* qkv, const void* o, const void* d_o, const float* 
   a.nwin = batch * g.nws * g.nws;
   a.units = a.nwin * g.heads;
   constexpr int smem = SM::kTotal + 1024;
-  static_assert(smem <= 227 * 1024, "attn_tc_bwd: shared memory budget");
+  static_assert(smem + SM::kStatic <= 227 * 1024, "attn_tc_bwd: shared memory budget");
   static bool done = false;
   if (!done) {
     SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -74,4 +74,53 @@ int scot_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* 
                               batch, res, ws, shift, heads, head_dim, (cudaStream_t)stream);
 }
 
+int scot_cast_f32_bf16(const float* in, void* out, long n, void* stream) {
+  return scot_cast_f32_bf16_launch(in, out, n, (cudaStream_t)stream);
+}
+int scot_embed_im2col(const float* x, void* out, int B, int Cin, int H, int W, int ps, void* stream) {
+  return scot_im2col_patch_launch(x, out, B, Cin, H, W, ps, (cudaStream_t)stream);
+}
+int scot_merge_gather(const float* x, const float* inp, void* out, int B, int res, int C, void* stream) {
+  return scot_merge_gather_launch(x, inp, out, B, res, C, (cudaStream_t)stream);
+}
+int scot_merge_scatter(const float* dG, const float* g_in, float* g_out, int B, int res, int C, void* stream) {
+  return scot_merge_scatter_launch(dG, g_in, g_out, B, res, C, (cudaStream_t)stream);
+}
+int scot_convnext_dwconv7_fwd(const float* x, const float* w, const float* bias, float* out, int B, int res, int C, void* stream) {
+  return scot_dwconv7_fwd_launch(x, w, bias, out, B, res, C, (cudaStream_t)stream);
+}
+int scot_convnext_dwconv7_bwd(const float* x, const float* w, const float* dout, const float* g_in, float* g_out, float* g_w,
+                              int B, int res, int C, void* stream) {
+  return scot_dwconv7_bwd_launch(x, w, dout, g_in, g_out, g_w, B, res, C, (cudaStream_t)stream);
+}
+int scot_convnext_scale_add_fwd(const float* in, const float* z, const float* gamma, float* out, void* zb, long rows, int C,
+                                void* stream) {
+  return scot_scale_add_fwd_launch(in, z, gamma, out, zb, rows, C, (cudaStream_t)stream);
+}
+int scot_convnext_scale_add_bwd(const float* g, const void* zb, const float* gamma, void* dz, float* g_gamma, float* g_bias,
+                                long rows, int C, void* stream) {
+  return scot_scale_add_bwd_launch(g, zb, gamma, dz, g_gamma, g_bias, rows, C, (cudaStream_t)stream);
+}
+int scot_recovery_unshuffle(const float* D, float* P, int B, int OC, int H, int W, int ps, void* stream) {
+  return scot_unshuffle_launch(D, P, B, OC, H, W, ps, (cudaStream_t)stream);
+}
+int scot_recovery_conv5_fwd(const float* P, const float* w, const float* resid, int resid_channels, const float* labels,
+                            const uint8_t* mask, int mask_mode, float* pred, int B, int OC, int H, int W, void* stream) {
+  return scot_conv5_fwd_launch(P, w, resid, resid_channels, labels, mask, mask_mode, pred, B, OC, H, W, (cudaStream_t)stream);
+}
+int scot_recovery_conv5_bwd(const float* P, const float* w, const float* dpred, float* dP_scratch, void* dD, float* g_w,
+                            float* g_bias, int B, int OC, int H, int W, int ps, void* stream) {
+  return scot_conv5_bwd_launch(P, w, dpred, dP_scratch, dD, g_w, g_bias, B, OC, H, W, ps, (cudaStream_t)stream);
+}
+int scot_loss_fwd(const float* pred, const float* labels, float* sums, float* loss, const int* slices_host, int n_slices, int p,
+                  int B, int OC, long HW, void* stream) {
+  return scot_loss_fwd_launch(pred, labels, sums, loss, slices_host, n_slices, p, B, OC, HW, (cudaStream_t)stream);
+}
+int scot_loss_bwd(const float* pred, const float* labels, const float* sums, const float* gscale, const float* extra,
+                  const uint8_t* mask, int mask_mode, float* dpred, const int* slices_host, int n_slices, int p, int B, int OC,
+                  long HW, void* stream) {
+  return scot_loss_bwd_launch(pred, labels, sums, gscale, extra, mask, mask_mode, dpred, slices_host, n_slices, p, B, OC, HW,
+                              (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -67,7 +67,7 @@ class FlatAdamW(torch.optim.Optimizer):
     """
 
     def __init__(self, params, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 max_grad_norm: Optional[float] = None, grad_scale: float = 1.0):
+                 max_grad_norm: Optional[float] = None, grad_scale: float = 1.0, allreduce: Optional[bool] = None):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid AdamW hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
@@ -76,8 +76,15 @@ class FlatAdamW(torch.optim.Optimizer):
         self.model = model
         self.max_grad_norm = max_grad_norm
         self.grad_scale = grad_scale
+        # Data parallelism. grad_mode="autograd" (default): the gradients reach `p.grad` through autograd, DDP / accelerate
+        # reduce them there and step() gathers them into the flat buffer. grad_mode="assign": `.grad` ARE views of the flat
+        # buffer and nobody has reduced them — with allreduce=True (or None = "auto": a process group with world_size > 1
+        # exists) step() sums the flat buffer over the ranks in ONE collective and scales by 1/world_size.
+        self.allreduce = allreduce
         self._bound = None
         self._step = 0
+        self._pending_state = None  # a state dict loaded before the flat buffers exist (HF Trainer resume)
+        self._hp_ring, self._hp_events, self._hp_slot = [], [], 0
 
     # ---- binding to the flat buffers -----------------------------------------------------------------
     def _bind(self):
@@ -106,8 +113,11 @@ class FlatAdamW(torch.optim.Optimizer):
         old = self._bound
         b = dict(flat=flat, gflat=gflat, chunk_group=cg.to(dev),
                  exp_avg=torch.zeros_like(flat), exp_avg_sq=torch.zeros_like(flat),
-                 hp_host=torch.zeros(len(self.param_groups), 8).pin_memory(),
                  hp=torch.zeros(len(self.param_groups), 8, device=dev), sq_norm=torch.zeros(1, device=dev))
+        # hyper-parameters travel through a RING of pinned host buffers guarded by events: with graph replay the host runs
+        # steps ahead of the device, a single buffer would be rewritten before its pending H2D copy has read it
+        self._hp_ring = [torch.zeros(len(self.param_groups), 8).pin_memory() for _ in range(4)]
+        self._hp_events = [None] * 4
         if old is not None:  # the model re-allocated its buffers (e.g. moved): carry the moments over
             b["exp_avg"].copy_(old["exp_avg"])
             b["exp_avg_sq"].copy_(old["exp_avg_sq"])
@@ -119,7 +129,39 @@ class FlatAdamW(torch.optim.Optimizer):
                                  "exp_avg": b["exp_avg"][off:off + p.numel()].view(p.shape),
                                  "exp_avg_sq": b["exp_avg_sq"][off:off + p.numel()].view(p.shape)}
         self._bound = b
+        if self._pending_state is not None:
+            pending, self._pending_state = self._pending_state, None
+            self.load_state_dict(pending)
         return b
+
+    def _gather_grads(self, b):
+        """Makes the flat gradient buffer hold what the optimizer must apply (see `allreduce` in __init__)."""
+        st = self.model._state
+        if getattr(self.model, "grad_mode", "assign") != "assign":
+            # autograd mode: the (possibly DDP-reduced, possibly accumulated) gradients live in p.grad
+            dst, src, missing = [], [], []
+            for p, gv in zip(st["plist"], st["gviews"]):
+                if p.grad is None:
+                    missing.append(gv)
+                elif p.grad.data_ptr() != gv.data_ptr():
+                    dst.append(gv)
+                    src.append(p.grad)
+            if dst:
+                torch._foreach_copy_(dst, src)
+            if missing:
+                torch._foreach_zero_(missing)
+            return self.grad_scale
+        scale = self.grad_scale
+        dist = torch.distributed
+        want = self.allreduce
+        if want is None:
+            want = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if want:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("FlatAdamW(allreduce=True) needs an initialised torch.distributed process group")
+            dist.all_reduce(b["gflat"])
+            scale = scale / dist.get_world_size()
+        return scale
 
     # ---- one optimizer step --------------------------------------------------------------------------
     @torch.no_grad()
@@ -129,15 +171,23 @@ class FlatAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         b = self._bind()
+        grad_scale = self._gather_grads(b)
         self._step += 1
         t = self._step
-        hp = b["hp_host"]
+        k = self._hp_slot
+        self._hp_slot = (k + 1) % len(self._hp_ring)
+        if self._hp_events[k] is not None:
+            self._hp_events[k].synchronize()  # the copy issued four steps ago has read this buffer
+        hp = self._hp_ring[k]
         for gid, g in enumerate(self.param_groups):
             b1, b2 = g["betas"]
             hp[gid, 0], hp[gid, 1], hp[gid, 2], hp[gid, 3], hp[gid, 4] = g["lr"], g["weight_decay"], b1, b2, g["eps"]
             hp[gid, 5] = 1.0 - b1 ** t
             hp[gid, 6] = math.sqrt(1.0 - b2 ** t)
         b["hp"].copy_(hp, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hp_events[k] = ev
         lib = _lib.load()
         stream = _lib.cur_stream()
         n = b["flat"].numel()
@@ -147,14 +197,15 @@ class FlatAdamW(torch.optim.Optimizer):
         _lib.check(lib.scot_adamw_step(_lib.ptr(b["flat"]), _lib.ptr(b["gflat"]), _lib.ptr(b["exp_avg"]),
                                        _lib.ptr(b["exp_avg_sq"]), None, _lib.ptr(b["chunk_group"]), n, _lib.ptr(b["hp"]),
                                        len(self.param_groups), _lib.ptr(b["sq_norm"]) if clip else None,
-                                       float(self.max_grad_norm or 0.0), float(self.grad_scale), stream), "scot_adamw_step")
+                                       float(self.max_grad_norm or 0.0), float(grad_scale), stream), "scot_adamw_step")
+        self._last_scale = float(grad_scale)
         for s in self.state.values():
             s["step"].fill_(float(t))
         return loss
 
     def grad_norm(self) -> torch.Tensor:
         """Total gradient norm of the last clipped step (device scalar; what clip_grad_norm_ returns)."""
-        return self._bound["sq_norm"].sqrt() * self.grad_scale
+        return self._bound["sq_norm"].sqrt() * getattr(self, "_last_scale", self.grad_scale)
 
     def zero_grad(self, set_to_none: bool = False):
         """Gradients are views of the flat buffer: clear it in one memset and keep the views bound."""
@@ -165,7 +216,12 @@ class FlatAdamW(torch.optim.Optimizer):
             super().zero_grad(set_to_none=set_to_none)
 
     def load_state_dict(self, state_dict):
-        """Loads a torch.optim.AdamW / FlatAdamW state dict: the moments are copied INTO the flat buffers."""
+        """Loads a torch.optim.AdamW / FlatAdamW state dict: the moments are copied INTO the flat buffers. Before the
+        model's first forward (HF Trainer restores the optimizer before the first step) the dict is kept and applied when
+        the flat buffers appear."""
+        if self.model._state is None:
+            self._pending_state = state_dict
+            return
         b = self._bind()
         groups = state_dict["param_groups"]
         if len(groups) != len(self.param_groups):

@@ -357,6 +357,10 @@ class _ScOTFunction(torch.autograd.Function):
         assign = model.grad_mode == "assign"
         if not assign:
             gflat.zero_()  # autograd accumulates the returned tensors into .grad itself
+        elif all(p.grad is None for p in st["plist"]):
+            # assign mode accumulates in place across micro-batches; `zero_grad(set_to_none=True)` (the torch / HF default)
+            # only drops the .grad views, so "every .grad is None" is the signal that a new accumulation window starts
+            gflat.zero_()
         slot = ctx.slot
         if slot is not None and slot.g_bwd is not None and gp is None:
             slot.gl.copy_(gl, non_blocking=True)
@@ -540,6 +544,13 @@ class ScOT(PreTrainedModel):
         self._state = dict(device=device, batch=batch, precision=self.precision, engine=eng, flat=flat, gflat=gflat,
                            plist=plist, views=views, gviews=gviews, arena=arena, slots={})
         return self._state
+
+    def zero_grad(self, set_to_none: bool = True):
+        """Also clears the flat gradient buffer the engine accumulates into (grad_mode="assign" binds .grad to its views)."""
+        if self._state is not None:
+            self._state["gflat"].zero_()
+        if set_to_none or self._state is None or self.grad_mode != "assign":
+            super().zero_grad(set_to_none=set_to_none)
 
     @property
     def flat_parameters(self) -> torch.Tensor:
