@@ -207,6 +207,13 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
  * grad_loss: device scalar or NULL; grad_pred: [B,Cout,H,W] or NULL. Gradients are accumulated, never zeroed. */
 int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void* arena, const float* grad_loss,
                          const float* grad_pred, int gemm_impl, void* stream);
+/* The backward pass in two parts, for overlapping the data-parallel gradient exchange with compute: part 1 (loss, patch
+ * recovery, decoder, ConvNeXt skips, deepest encoder stage) leaves the gradients of flat elements
+ * [scot_engine_grad_split(), scot_engine_param_elems()) final — ~85 % of the bytes of the shipped models —, part 2 (remaining
+ * encoder stages, embeddings) the rest. part 0 = both (== scot_engine_backward). */
+int scot_engine_backward_part(ScotEngine* e, const float* params, float* grads, void* arena, const float* grad_loss,
+                              const float* grad_pred, int gemm_impl, int part, void* stream);
+long scot_engine_grad_split(const ScotEngine* e);
 /* ---- fused optimizer step on the flat buffers (replaces accelerate clip_grad_norm_ + torch.optim.AdamW,
  * scOT/train.py:286, scOT/trainer.py:295-445) ----------------------------------------------------------------------
  * out[0] = sum(grads^2) (cleared first). */

@@ -169,6 +169,10 @@ def _declare_engine(lib):
     lib.scot_engine_backward.restype = i
     lib.scot_engine_bind_io.argtypes = [vp] * 5 + [i, vp]
     lib.scot_engine_bind_io.restype = i
+    lib.scot_engine_backward_part.argtypes = [vp] * 6 + [i, i, vp]
+    lib.scot_engine_backward_part.restype = i
+    lib.scot_engine_grad_split.argtypes = [vp]
+    lib.scot_engine_grad_split.restype = l
     lib.scot_grad_sq_norm.argtypes = [vp, l, vp, vp]
     lib.scot_grad_sq_norm.restype = i
     lib.scot_adamw_step.argtypes = [vp] * 6 + [l, vp, i, vp, f, f, vp]
@@ -355,6 +359,12 @@ class Engine:
         check(self._lib.scot_engine_bind_io(self.handle, ptr(pixel_values), ptr(time), ptr(labels), ptr(mask), mask_mode,
                                             ptr(pred)), "scot_engine_bind_io")
 
-    def backward(self, params, grads, arena, grad_loss, grad_pred, impl=GEMM_TCGEN05):
-        check(self._lib.scot_engine_backward(self.handle, ptr(params), ptr(grads), ptr(arena), ptr(grad_loss),
-                                             ptr(grad_pred), impl, cur_stream()), "scot_engine_backward")
+    def backward(self, params, grads, arena, grad_loss, grad_pred, impl=GEMM_TCGEN05, part=0):
+        """part 0: whole backward; 1 / 2: the two halves of scot_engine_backward_part (gradient elements
+        [grad_split, end) are final after part 1)"""
+        check(self._lib.scot_engine_backward_part(self.handle, ptr(params), ptr(grads), ptr(arena), ptr(grad_loss),
+                                                  ptr(grad_pred), impl, part, cur_stream()), "scot_engine_backward")
+
+    @property
+    def grad_split(self) -> int:
+        return int(self._lib.scot_engine_grad_split(self.handle))

@@ -94,7 +94,11 @@ struct ScotEngine {
   size_t dzbB, dzb2B, dqkvB, dhB, dobB;  // second set of block-backward scratch (blocks alternate, see block_bwd)
   size_t partial_bytes;
   std::vector<size_t> gstage;            // fp32 [M_s, C_s]
-  std::vector<ScotCpbTable> cpb_tables;  // relative-position-bias MLPs of all attention layers (<= 64 per table)
+  // relative-position-bias MLPs of all attention layers (<= 64 per table), split by WHEN their gradients are final in the
+  // backward pass: "early" = decoder + deepest encoder stage, "late" = the remaining encoder stages (see
+  // scot_engine_backward_part)
+  std::vector<ScotCpbTable> cpb_early, cpb_late;
+  long split_elem = 0;  // flat-buffer offset of the first parameter of the deepest encoder stage
   // forward state needed by backward
   const float* last_pixels = nullptr;
   const float* last_time = nullptr;
@@ -219,6 +223,8 @@ int build_params(ScotEngine* e) {
       e->merge[s].norm = R.norm(pre + ".norm", 2L * g.C, cond);
     }
   }
+  e->split_elem = e->enc[e->ns - 1].empty() ? R.cursor : e->enc[e->ns - 1][0].ls;  // first parameter of the deepest stage
+  e->split_elem = e->split_elem / 64 * 64;
   e->dec.resize(e->ns);
   e->unmerge.resize(e->ns);
   for (int j = 0; j < e->ns; ++j) {
@@ -391,8 +397,8 @@ int build_plan(ScotEngine* e) {
     for (auto& bb : e->dbuf[j]) plan_dpre(bb, e->geo[e->ns - 1 - j]);
   // descriptor tables for the batched bias-MLP kernels
   {
-    std::vector<ScotCpbLayer> all;
-    auto add_layer = [&](const BlockP& p, const BlockBuf& bb, const Geo& g) {
+    std::vector<ScotCpbLayer> late, early;
+    auto add_layer = [&](std::vector<ScotCpbLayer>& all, const BlockP& p, const BlockBuf& bb, const Geo& g) {
       ScotCpbLayer L;
       L.w1 = (int)p.cw1; L.b1 = (int)p.cb1; L.w2 = (int)p.cw2; L.ls = (int)p.ls;
       L.tab2 = (int)(bb.tab2 / 256); L.alpha = (int)(bb.alpha / 256);
@@ -401,16 +407,20 @@ int build_plan(ScotEngine* e) {
       all.push_back(L);
     };
     for (int s = 0; s < e->ns; ++s)
-      for (int i = 0; i < e->geo[s].depth; ++i) add_layer(e->enc[s][i], e->ebuf[s][i], e->geo[s]);
+      for (int i = 0; i < e->geo[s].depth; ++i) add_layer(s == e->ns - 1 ? early : late, e->enc[s][i], e->ebuf[s][i], e->geo[s]);
     for (int j = 0; j < e->ns; ++j)
-      for (int i = 0; i < e->geo[e->ns - 1 - j].depth; ++i) add_layer(e->dec[j][i], e->dbuf[j][i], e->geo[e->ns - 1 - j]);
-    for (size_t i = 0; i < all.size(); i += SCOT_CPB_MAX_LAYERS) {
-      ScotCpbTable t;
-      memset(&t, 0, sizeof(t));
-      t.n = (int)std::min<size_t>(SCOT_CPB_MAX_LAYERS, all.size() - i);
-      for (int k = 0; k < t.n; ++k) t.layer[k] = all[i + k];
-      e->cpb_tables.push_back(t);
-    }
+      for (int i = 0; i < e->geo[e->ns - 1 - j].depth; ++i) add_layer(early, e->dec[j][i], e->dbuf[j][i], e->geo[e->ns - 1 - j]);
+    auto pack = [&](const std::vector<ScotCpbLayer>& all, std::vector<ScotCpbTable>& out) {
+      for (size_t i = 0; i < all.size(); i += SCOT_CPB_MAX_LAYERS) {
+        ScotCpbTable t;
+        memset(&t, 0, sizeof(t));
+        t.n = (int)std::min<size_t>(SCOT_CPB_MAX_LAYERS, all.size() - i);
+        for (int k = 0; k < t.n; ++k) t.layer[k] = all[i + k];
+        out.push_back(t);
+      }
+    };
+    pack(early, e->cpb_early);
+    pack(late, e->cpb_late);
   }
   e->gstage.resize(e->ns);
   for (int s = 0; s < e->ns; ++s) e->gstage[s] = b.take((size_t)e->geo[s].M * e->geo[s].C * 4);
@@ -792,7 +802,8 @@ int scot_engine_forward(ScotEngine* e, const float* params, void* arena, const f
   // bf16 copy of all parameters (GEMM operands)
   RC(scot_cast_f32_bf16_launch(params, c.at<bf16>(e->wb16), e->n_elems, c.st));
   // relative-position-bias tables of every attention layer (batch independent), one launch
-  for (const ScotCpbTable& t : e->cpb_tables) RC(scot_cpb_fwd_launch(&t, params, arena, c.st));
+  for (const ScotCpbTable& t : e->cpb_early) RC(scot_cpb_fwd_launch(&t, params, arena, c.st));
+  for (const ScotCpbTable& t : e->cpb_late) RC(scot_cpb_fwd_launch(&t, params, arena, c.st));
   // ---- embeddings (scOT/model.py:295-310, 345-366) ----
   const int K0 = d.num_channels * d.patch_size * d.patch_size;
   RC(scot_im2col_patch_launch(pixel_values, c.at<bf16>(e->p16), B, d.num_channels, d.image_size, d.image_size, d.patch_size,
@@ -910,10 +921,23 @@ int scot_engine_bind_io(ScotEngine* e, const float* pixel_values, const float* t
 
 int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void* arena, const float* grad_loss,
                          const float* grad_pred, int gemm_impl, void* stream) {
+  return scot_engine_backward_part(e, params, grads, arena, grad_loss, grad_pred, gemm_impl, 0, stream);
+}
+
+long scot_engine_grad_split(const ScotEngine* e) { return e ? e->split_elem : 0; }
+
+// part 0: the whole backward pass. part 1: loss, recovery, decoder, ConvNeXt skips and the deepest encoder stage — when it
+// returns (all side streams joined) the gradients of flat elements [scot_engine_grad_split(), end) are final; part 2: the
+// remaining encoder stages and the embeddings, elements [0, split). Data parallel training all-reduces the first range on
+// a communication stream while part 2 computes (runtime.GraphedTrainStep).
+int scot_engine_backward_part(ScotEngine* e, const float* params, float* grads, void* arena, const float* grad_loss,
+                              const float* grad_pred, int gemm_impl, int part, void* stream) {
   SCOT_REQUIRE(e && params && grads && arena, "engine_backward: null pointer");
+  SCOT_REQUIRE(part >= 0 && part <= 2, "engine_backward: part must be 0, 1 or 2");
+  const bool do1 = part != 2, do2 = part != 1;
   SCOT_REQUIRE(e->have_forward, "engine_backward: call scot_engine_forward first");
-  SCOT_REQUIRE(grad_loss != nullptr || grad_pred != nullptr, "engine_backward: need grad_loss and/or grad_pred");
-  SCOT_REQUIRE(grad_loss == nullptr || e->last_labels != nullptr, "engine_backward: grad_loss given but forward had no labels");
+  SCOT_REQUIRE(!do1 || grad_loss != nullptr || grad_pred != nullptr, "engine_backward: need grad_loss and/or grad_pred");
+  SCOT_REQUIRE(!do1 || grad_loss == nullptr || e->last_labels != nullptr, "engine_backward: grad_loss given but forward had no labels");
   const ScotModelDesc& d = e->d;
   Ctx c{e, params, grads, (uint8_t*)arena, e->last_time, (cudaStream_t)stream, gemm_impl};
   SplitGuard split_guard(e->split_off);
@@ -944,6 +968,7 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
     SCOT_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_afork, cudaEventDisableTiming));
     SCOT_CHECK_CUDA(cudaEventCreateWithFlags(&e->ev_ajoin, cudaEventDisableTiming));
   }
+  if (do1) {
   SCOT_CHECK_CUDA(cudaMemsetAsync(c.at<uint8_t>(e->dgrads_zero_begin), 0, e->dgrads_zero_bytes, c.st));
   // ---- loss + patch recovery backward ----
   float* dpred = c.at<float>(e->dpred);
@@ -1005,8 +1030,10 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
   for (int s = 0; s < ns; ++s)
     if (d.skip_blocks[s] > 0 && !cnx_on_side(e, s))
       RC(cnx_bwd_stage(c, s, c.at<float>(e->gstage[s]), cnx_scratch(c, false)));
+  }  // do1
   // ---- encoder backward (coarsest stage first) ----
   for (int s = ns - 1; s >= 0; --s) {
+    if (!(s == ns - 1 ? do1 : do2)) continue;
     const Geo& g = e->geo[s];
     float* gr = c.at<float>(e->gstage[s]);
     RC(cnx_join(c, s));  // ConvNeXt backward of this stage's skip (side branch) has updated gstage[s]
@@ -1035,7 +1062,13 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
       // the stage input also feeds the merge through `hidden + inputs` (model.py:847-849)
       RC(scot_merge_scatter_launch(c.at<float>(e->z32), gr, gr, B, g.res, g.C, c.st));
     }
+    if (s == ns - 1) {
+      // end of part 1: every side branch joins here, then the bias-MLP / logit-scale gradients of the layers done so far
+      RC(cnx_join_all(c));
+      for (const ScotCpbTable& t : e->cpb_early) RC(scot_cpb_bwd_launch(&t, params, grads, arena, c.st));
+    }
   }
+  if (!do2) return 0;
   RC(cnx_join_all(c));
   // ---- embeddings backward ----
   {
@@ -1046,7 +1079,7 @@ int scot_engine_backward(ScotEngine* e, const float* params, float* grads, void*
     RC(gemm(c, dzb, g0.C, 1, c.at<bf16>(e->p16), K0, 1, g0.C, K0, g0.M, SCOT_EPI_ATOMIC_F32, nullptr, c.g(e->emb_w), K0));
   }
   // ---- relative-position-bias MLPs + logit scales of all attention layers (batched) ----
-  for (const ScotCpbTable& t : e->cpb_tables) RC(scot_cpb_bwd_launch(&t, params, grads, arena, c.st));
+  for (const ScotCpbTable& t : e->cpb_late) RC(scot_cpb_bwd_launch(&t, params, grads, arena, c.st));
   return 0;
 }
 

@@ -4,6 +4,9 @@ data-parallel gradient exchange (one NCCL all-reduce over the flat gradient buff
 The reference gets its data parallelism from accelerate -> torch DDP (~25 bucketed all-reduces per step,
 SURVEY.md §2 row 11); here the gradients already live in one flat buffer, so a step is
     graph replay (zero grads, forward, backward)  ->  all_reduce(flat_grads)  [-> optimizer].
+With more than one rank the backward graph is cut where ~85 % of the gradient bytes are final (decoder, ConvNeXt skips,
+deepest encoder stage: one contiguous range of the flat buffer): that range is all-reduced on a communication stream
+while the rest of the backward pass runs, the small remainder afterwards — two NCCL calls, one of them hidden.
 """
 from __future__ import annotations
 
@@ -24,7 +27,8 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model: ScOT, batch: int, device: Optional[torch.device] = None, use_mask: bool = False,
-                 use_graph: bool = True, world_size: int = 1, average: bool = True, optimizer=None):
+                 use_graph: bool = True, world_size: int = 1, average: bool = True, optimizer=None,
+                 overlap_allreduce: Optional[bool] = None):
         cfg = model.config
         self.model = model
         self.device = device or next(model.parameters()).device
@@ -44,6 +48,12 @@ class GraphedTrainStep:
         # d(loss)/d(loss): pre-scaled by 1/world so that the summed all-reduce yields the DDP mean
         self.gscale = torch.full((1,), (1.0 / world_size) if average else 1.0, device=self.device)
         self.graph = None
+        self.graph2 = None
+        # overlap of the gradient exchange with the tail of the backward pass (default: whenever there is an exchange)
+        self.overlap = (world_size > 1) if overlap_allreduce is None else bool(overlap_allreduce)
+        self.split = st["engine"].grad_split if self.overlap else 0
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.overlap else None
+        self.mid_event = torch.cuda.Event() if self.overlap else None
         self.optimizer = optimizer  # e.g. poseidon_b200.optim.FlatAdamW: fused clip + AdamW on the flat buffers
         self._impl = model.gemm_impl
         # bind .grad to the flat views once; the graph zeroes and refills the same memory every step
@@ -52,12 +62,14 @@ class GraphedTrainStep:
         if use_graph:
             self._capture()
 
-    def _body(self):
+    def _body(self, part: int = 0):
+        """part 0: everything; 1: zero grads + forward + first part of the backward; 2: rest of the backward"""
         st = self.st
-        st["gflat"].zero_()
-        st["engine"].forward(st["flat"], st["arena"], self.x, self.t, self.y, self.mask, 1 if self.mask is not None else 0,
-                             self.pred, self.loss, self._impl)
-        st["engine"].backward(st["flat"], st["gflat"], st["arena"], self.gscale, None, self._impl)
+        if part != 2:
+            st["gflat"].zero_()
+            st["engine"].forward(st["flat"], st["arena"], self.x, self.t, self.y, self.mask, 1 if self.mask is not None else 0,
+                                 self.pred, self.loss, self._impl)
+        st["engine"].backward(st["flat"], st["gflat"], st["arena"], self.gscale, None, self._impl, part=part)
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)
@@ -68,8 +80,15 @@ class GraphedTrainStep:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
+        if not self.overlap:
+            with torch.cuda.graph(self.graph):
+                self._body()
+            return
         with torch.cuda.graph(self.graph):
-            self._body()
+            self._body(1)
+        self.graph2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph2, pool=self.graph.pool()):
+            self._body(2)
 
     def load_batch(self, pixel_values, time, labels, pixel_mask=None, non_blocking=True):
         self.x.copy_(pixel_values, non_blocking=non_blocking)
@@ -80,15 +99,38 @@ class GraphedTrainStep:
             self.mask.copy_(pixel_mask.to(torch.uint8), non_blocking=non_blocking)
 
     def run(self):
+        if not self.overlap:
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._body()
+            return
         if self.graph is not None:
             self.graph.replay()
         else:
-            self._body()
+            self._body(1)
+        self.mid_event.record()  # gradients [split, end) are final from here on
+        if self.world_size > 1:
+            self.comm_stream.wait_event(self.mid_event)
+            with torch.cuda.stream(self.comm_stream):
+                torch.distributed.all_reduce(self.st["gflat"][self.split:])
+        if self.graph2 is not None:
+            self.graph2.replay()
+        else:
+            self._body(2)
 
     def allreduce(self):
-        """The single gradient collective of a data-parallel step (NCCL over NVLink/NVSwitch)."""
-        if self.world_size > 1:
+        """The gradient exchange of a data-parallel step (NCCL over NVLink / NVSwitch): one all-reduce of the flat buffer,
+        or — overlapped mode — the remainder [0, split) plus the join with the communication stream, on which the bulk
+        [split, end) has been in flight since the middle of the backward pass."""
+        if self.world_size <= 1:
+            return
+        if not self.overlap:
             torch.distributed.all_reduce(self.st["gflat"])
+            return
+        if self.split > 0:
+            torch.distributed.all_reduce(self.st["gflat"][:self.split])
+        torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
 
     def optimizer_step(self):
         """clip_grad_norm_ + AdamW on the flat buffers (two launches), after the gradient all-reduce."""
@@ -104,7 +146,7 @@ class GraphedTrainStep:
     def launches_per_step(self) -> int:
         lib = _lib.load()
         before = lib.scot_launch_count()
-        self._body()
+        self._body()  # part 0 == parts 1 + 2
         torch.cuda.synchronize(self.device)
         return int(lib.scot_launch_count() - before)
 

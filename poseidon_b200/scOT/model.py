@@ -112,9 +112,43 @@ class LayerNorm(nn.LayerNorm):
         return super().forward(x)
 
 
+class _ClnFunction(torch.autograd.Function):
+    """Stand-alone ConditionalLayerNorm through the same CUDA kernels the engine uses (scot_cln_fwd / scot_cln_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, time, aw, ab, cw, cb, eps):
+        C = x.shape[-1]
+        xs = x.detach().to(torch.float32).contiguous()
+        rows = xs.numel() // C
+        t = time.detach().reshape(-1).to(device=x.device, dtype=torch.float32).contiguous()
+        if rows % t.numel():
+            raise ValueError("ConditionalLayerNorm: time must have one entry per sample")
+        rps = rows // t.numel()
+        f = lambda v: v.detach().reshape(-1).to(torch.float32).contiguous()  # noqa: E731
+        aw_, ab_, cw_, cb_ = f(aw), f(ab), f(cw), f(cb)
+        y = torch.empty_like(xs)
+        zhat = torch.empty(xs.shape, device=x.device, dtype=torch.bfloat16)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        _lib.cln_fwd(xs, None, t, aw_, ab_, cw_, cb_, y, None, zhat, rstd, rows, C, rps, 0, eps)
+        ctx.save_for_backward(zhat, rstd, t, aw_, ab_)
+        ctx.meta = (rows, C, rps, x.shape, aw.shape, ab.shape)
+        return y.view(x.shape).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        zhat, rstd, t, aw_, ab_ = ctx.saved_tensors
+        rows, C, rps, xshape, wshape, bshape = ctx.meta
+        dys = dy.detach().to(torch.float32).contiguous()
+        dz = torch.empty(rows, C, device=dy.device, dtype=torch.float32)
+        g = [torch.zeros(C, device=dy.device, dtype=torch.float32) for _ in range(4)]
+        _lib.cln_bwd(dys, zhat, rstd, t, aw_, ab_, dz, True, g[0], g[1], g[2], g[3], None, rows, C, rps, 0)
+        return dz.view(xshape).to(dy.dtype), None, g[0].view(wshape), g[1].view(bshape), g[2].view(wshape), g[3].view(bshape), None
+
+
 class ConditionalLayerNorm(nn.Module):
-    """reference scOT/model.py:143-160. The torch forward below is only for stand-alone use of the class;
-    inside ScOT the fused CUDA kernel (csrc/norm.cu) evaluates it."""
+    """reference scOT/model.py:143-160: same parameters (two Linear(1, dim)), same call signature. The arithmetic is the
+    fused CUDA kernel of csrc/norm.cu — inside ScOT the engine calls it directly, stand-alone use goes through
+    `_ClnFunction`. There is no torch / CPU evaluation path."""
 
     def __init__(self, dim, eps=1e-5):
         super().__init__()
@@ -123,16 +157,9 @@ class ConditionalLayerNorm(nn.Module):
         self.bias = nn.Linear(1, dim)
 
     def forward(self, x, time):
-        mean = x.mean(dim=-1, keepdim=True)
-        var = (x ** 2).mean(dim=-1, keepdim=True) - mean ** 2
-        x = (x - mean) / (var + self.eps).sqrt()
-        time = time.reshape(-1, 1).type_as(x)
-        weight = self.weight(time).unsqueeze(1)
-        bias = self.bias(time).unsqueeze(1)
-        if x.dim() == 4:
-            weight = weight.unsqueeze(1)
-            bias = bias.unsqueeze(1)
-        return weight * x + bias
+        if not x.is_cuda:
+            raise RuntimeError("poseidon_b200 ConditionalLayerNorm runs on a CUDA (sm_100a) device only")
+        return _ClnFunction.apply(x, time, self.weight.weight, self.weight.bias, self.bias.weight, self.bias.bias, self.eps)
 
 
 def _norm(config, dim, eps=None):

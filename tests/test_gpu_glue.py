@@ -207,3 +207,30 @@ def test_attention_token_map_is_exact(L):
         # averages of {0,1} bits over 16 .. 256 tokens: multiples of 1/256, exactly representable; the kernel's P is
         # exp2(0) / count in fp32 -> bf16 products are exact up to the final bf16 rounding of the mean
         assert torch.equal(out.float(), o.reshape(M, hd).bfloat16().float()), (Bn, res, ws, shift)
+
+
+def test_standalone_conditional_layer_norm_module():
+    """the drop-in ConditionalLayerNorm class (scOT/model.py:143-160) evaluated stand-alone runs the CUDA kernels"""
+    from poseidon_b200.scOT.model import ConditionalLayerNorm
+
+    torch.manual_seed(0)
+    m = ConditionalLayerNorm(96).cuda()
+    with torch.no_grad():
+        m.weight.bias.fill_(1.0)
+        m.weight.weight.normal_(0, 0.2)
+        m.bias.weight.normal_(0, 0.2)
+    x = torch.randn(3, 8, 8, 96, device=dev, requires_grad=True)
+    t = torch.rand(3, device=dev)
+    y = m(x, t)
+    mean = x.mean(-1, keepdim=True)
+    var = (x ** 2).mean(-1, keepdim=True) - mean ** 2
+    xn = (x - mean) / (var + 1e-5).sqrt()
+    tt = t.reshape(-1, 1)
+    ref = m.weight(tt).view(3, 1, 1, 96) * xn + m.bias(tt).view(3, 1, 1, 96)
+    assert rel(y, ref) < 1e-5
+    g = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(ref, [x, m.weight.weight], g, retain_graph=True)
+    y.backward(g)
+    assert rel(x.grad, gx) < 6e-3 and rel(m.weight.weight.grad, gw) < 6e-3  # zhat is saved in bf16
+    with pytest.raises(RuntimeError):
+        m.cpu()(x.detach().cpu(), t.cpu())

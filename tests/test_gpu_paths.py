@@ -26,7 +26,9 @@ def rel(a, b):
 BASE = dict(image_size=32, patch_size=4, num_channels=3, num_out_channels=3, embed_dim=32, depths=[2, 2], num_heads=[2, 4],
             skip_connections=[1, 0], window_size=4, mlp_ratio=4.0, drop_path_rate=0.0, use_conditioning=True, p=1,
             channel_slice_list_normalized_loss=[0, 1, 3], residual_model="convnext", learn_residual=False)
-TOL = {"parity": (2e-4, 2e-3), "bf16": (3e-2, 8e-2)}  # (output / loss, global gradient)
+# (output / loss, global gradient). The objective contains the L1 loss: in bf16 a prediction that lands on the other side of
+# its label flips sign(pred - label), so the bf16 gradient bound is looser than the smooth-objective bound of test_gpu_model
+TOL = {"parity": (2e-4, 2e-3), "bf16": (3e-2, 0.15)}
 
 
 def build(precision, **over):
