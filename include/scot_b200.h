@@ -170,6 +170,30 @@ int scot_loss_bwd(const float* pred, const float* labels, const float* sums, con
                   const uint8_t* mask, int mask_mode, float* dpred, const int* slices_host, int n_slices, int p, int B, int OC,
                   long HW, void* stream);
 
+/* ---- one ScOTLayer (scOT/model.py:500-581: shifted-window cosine attention + res-post-norm + MLP) ------------------------
+ * Stand-alone form of the block the engine sequences. x, y, dy, dx: [batch*res*res, C] f32.
+ * `params` / `grads`: scot_layer_num_params() device pointers to fp32 tensors in the reference's state_dict order of a layer
+ * (attention.self.logit_scale, continuous_position_bias_mlp.0.{weight,bias}, .2.weight, query.{weight,bias}, key.weight,
+ * value.{weight,bias}, attention.output.dense.{weight,bias}, layernorm_before.*, intermediate.dense.{weight,bias},
+ * output.dense.{weight,bias}, layernorm_after.*; a norm is {weight.weight, weight.bias, bias.weight, bias.bias} when
+ * conditioned, {weight, bias} otherwise). The workspace (scot_layer_workspace_bytes, 256 B aligned, caller-owned) keeps the
+ * parameters' flat copy and everything scot_layer_bwd needs; bwd overwrites grads[i] (NULL entries are skipped). */
+typedef struct ScotLayerDesc {
+  int batch, res, C, heads;
+  int window;  /* effective window: min(window_size, res) */
+  int shift;   /* 0 or window / 2 */
+  float mlp_ratio;
+  int use_conditioning;
+  float layer_norm_eps;
+  int precision; /* 0 bf16, 1 parity (split-bf16) */
+} ScotLayerDesc;
+int scot_layer_num_params(const ScotLayerDesc* desc);
+size_t scot_layer_workspace_bytes(const ScotLayerDesc* desc);
+int scot_layer_fwd(const ScotLayerDesc* desc, const void* const* params, const float* x, const float* time, float* y,
+                   void* workspace, size_t ws_bytes, void* stream);
+int scot_layer_bwd(const ScotLayerDesc* desc, void* const* grads, const float* time, const float* dy, float* dx, void* workspace,
+                   size_t ws_bytes, void* stream);
+
 /* ---- whole-model engine --------------------------------------------------------------------------
  * Mirrors ScOTConfig (scOT/model.py:66-132); replaces ScOT.forward (:1318-1509) + autograd backward. */
 typedef struct ScotModelDesc {

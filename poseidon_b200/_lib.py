@@ -119,6 +119,11 @@ class ScotModelDesc(C.Structure):
     ]
 
 
+class ScotLayerDesc(C.Structure):
+    _fields_ = [("batch", C.c_int), ("res", C.c_int), ("C", C.c_int), ("heads", C.c_int), ("window", C.c_int), ("shift", C.c_int),
+                ("mlp_ratio", C.c_float), ("use_conditioning", C.c_int), ("layer_norm_eps", C.c_float), ("precision", C.c_int)]
+
+
 class ScotWgradProblem(C.Structure):
     _fields_ = [("dY", C.c_void_p), ("ld_dy", C.c_long), ("X", C.c_void_p), ("ld_x", C.c_long), ("dW", C.c_void_p),
                 ("ld_dw", C.c_long), ("tokens", C.c_long), ("n_out", C.c_int), ("n_in", C.c_int)]
@@ -179,6 +184,14 @@ def _declare_engine(lib):
     lib.scot_adamw_step.restype = i
     lib.scot_lp_plane_sums.argtypes = [vp, vp, vp, i, l, l, vp]
     lib.scot_lp_plane_sums.restype = i
+    lib.scot_layer_num_params.argtypes = [C.POINTER(ScotLayerDesc)]
+    lib.scot_layer_num_params.restype = i
+    lib.scot_layer_workspace_bytes.argtypes = [C.POINTER(ScotLayerDesc)]
+    lib.scot_layer_workspace_bytes.restype = C.c_size_t
+    lib.scot_layer_fwd.argtypes = [C.POINTER(ScotLayerDesc), C.POINTER(vp), vp, vp, vp, vp, C.c_size_t, vp]
+    lib.scot_layer_fwd.restype = i
+    lib.scot_layer_bwd.argtypes = [C.POINTER(ScotLayerDesc), C.POINTER(vp), vp, vp, vp, vp, C.c_size_t, vp]
+    lib.scot_layer_bwd.restype = i
     # glue ops
     for name, args in (
         ("scot_cast_f32_bf16", [vp, vp, l, vp]),
@@ -311,6 +324,44 @@ def attn_bwd(qkv, o, d_o, lse, tab2, alpha, dqkv, partial, dtab, dalpha, g_qbias
     check(load().scot_attn_bwd(ptr(qkv), ptr(o), ptr(d_o), ptr(lse), ptr(tab2), ptr(alpha), ptr(dqkv), ptr(partial),
                                partial.numel() * partial.element_size(), ptr(dtab), ptr(dalpha), ptr(g_qbias),
                                ptr(g_vbias), batch, res, ws, shift, heads, hd, cur_stream()), "scot_attn_bwd")
+
+
+class Layer:
+    """Stand-alone ScOTLayer through scot_layer_fwd / scot_layer_bwd. `params`: list of fp32 CUDA tensors in the reference's
+    state_dict order of a layer (see scot_b200.h)."""
+
+    def __init__(self, batch, res, Cdim, heads, window, shift, mlp_ratio=4.0, use_conditioning=True, eps=1e-5, precision=0):
+        import torch
+
+        self.desc = ScotLayerDesc(batch, res, Cdim, heads, window, shift, mlp_ratio, int(use_conditioning), eps, precision)
+        lib = load()
+        self.n = lib.scot_layer_num_params(C.byref(self.desc))
+        nbytes = lib.scot_layer_workspace_bytes(C.byref(self.desc))
+        if nbytes == 0:
+            check(1, "scot_layer_workspace_bytes")
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
+        shift_ = (-ws.data_ptr()) % 256
+        self.ws = ws[shift_:shift_ + nbytes]
+        self.rows, self.C = batch * res * res, Cdim
+
+    def forward(self, params, x, time):
+        import torch
+
+        assert len(params) == self.n
+        arr = (C.c_void_p * self.n)(*[p.data_ptr() for p in params])
+        y = torch.empty(self.rows, self.C, device=x.device)
+        check(load().scot_layer_fwd(C.byref(self.desc), arr, ptr(x), ptr(time), ptr(y), ptr(self.ws), self.ws.numel(),
+                                    cur_stream()), "scot_layer_fwd")
+        return y
+
+    def backward(self, grads, time, dy):
+        import torch
+
+        arr = (C.c_void_p * self.n)(*[g.data_ptr() if g is not None else None for g in grads])
+        dx = torch.empty(self.rows, self.C, device=dy.device)
+        check(load().scot_layer_bwd(C.byref(self.desc), arr, ptr(time), ptr(dy), ptr(dx), ptr(self.ws), self.ws.numel(),
+                                    cur_stream()), "scot_layer_bwd")
+        return dx
 
 
 def glue(name, *args):

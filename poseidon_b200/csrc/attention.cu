@@ -496,8 +496,8 @@ __device__ __forceinline__ void fold_bias_to_table(const float* __restrict__ sac
   }
 }
 
-// Same fold for 16 x 16 windows with the address arithmetic taken out of the inner loop (ATTN_DQ_FOLD2 candidate, not yet
-// run on hardware): a slot address splits into f(m) + g(n) with n = m - (16 dp + dq), and stepping one window row down
+// Same fold for 16 x 16 windows with the address arithmetic taken out of the inner loop (validated on B200 in round 2:
+// bit-compatible gradients, -0.19 ms per Poseidon-B step, profiles/r02_bringup_summary.txt): a slot address splits into f(m) + g(n) with n = m - (16 dp + dq), and stepping one window row down
 // (m += 16, n += 16) adds the constant 16 N + 256. Per (query, key) pair the loop below is one LDS, one FADD and one
 // pointer add instead of ~20 integer instructions — the fold is 14 % of the dq kernel's executed instructions
 // (profiles/r01_ncu_full_summary.md). Summation order differs from fold_bias_to_table (fp32 reassociation only).
@@ -550,9 +550,7 @@ struct DqCfg {
                                  + (size_t)TABN * 4 + (size_t)NWARP * 16 * 4 /*inv norms*/;
 };
 
-// FOLD2 (SCOT_ATTN_DQ_FOLD2=1, 16 x 16 windows only): bias-gradient fold with fold_bias_to_table16 — candidate, never run on
-// hardware; the default instantiations (FOLD2 = false) compile to the same SASS as before the parameter existed.
-template <int WS, int HD, int NWARP, bool SHIFT, bool FOLD2 = false>
+template <int WS, int HD, int NWARP, bool SHIFT>
 __global__ void __launch_bounds__(NWARP * 32)
 attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf, const bf16* __restrict__ do_buf,
                    const float* __restrict__ lse, const float* __restrict__ tab2, const float* __restrict__ alpha,
@@ -733,7 +731,7 @@ attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o_buf,
   // fold this CTA's bias-gradient accumulators (fragment order, summed over its windows) onto the (2ws-1)^2 table of
   // the head through the relative position index (HF:512-523) and add the <= 961 table entries to the layer's
   // gradient table: a gather per table entry, no N x N round trip through global memory, no second kernel
-  if constexpr (FOLD2 && WS == 16) fold_bias_to_table16<NWARP>(sacc, dtab, h, g.heads, rg, tid, nthreads);
+  if constexpr (WS == 16) fold_bias_to_table16<NWARP>(sacc, dtab, h, g.heads, rg, tid, nthreads);
   else fold_bias_to_table<WS, NWARP>(sacc, dtab, h, g.heads, rg, tid, nthreads);
   acc_alpha = warp_sum(acc_alpha);
   if (lane == 0) atomicAdd(dalpha + h, acc_alpha);
@@ -1016,18 +1014,6 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
   }
   void (*k1)(const bf16*, const bf16*, const bf16*, const float*, const float*, const float*, bf16*, float*, float*, float*,
              WinGeom, int, int) = g.shift > 0 ? attn_bwd_dq_kernel<WS, HD, NWARP, true> : attn_bwd_dq_kernel<WS, HD, NWARP, false>;
-  if constexpr (WS == 16) {
-    const char* ev = getenv("SCOT_ATTN_DQ_FOLD2");  // candidate, read per launch
-    if (ev != nullptr && ev[0] == '1') {
-      static bool done2 = false;
-      if (!done2) {
-        SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<WS, HD, NWARP, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::smem));
-        SCOT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<WS, HD, NWARP, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::smem));
-        done2 = true;
-      }
-      k1 = g.shift > 0 ? attn_bwd_dq_kernel<WS, HD, NWARP, true, true> : attn_bwd_dq_kernel<WS, HD, NWARP, false, true>;
-    }
-  }
   auto k2 = g.shift > 0 ? attn_bwd_dkv_kernel<WS, HD, NWARP, true> : attn_bwd_dkv_kernel<WS, HD, NWARP, false>;
   // dq kernel: ~200 KB of smem -> one CTA per SM, so size the grid to a single wave; fewer chunks also means
   // fewer bias-gradient dumps for the second-stage reduction
@@ -1123,12 +1109,6 @@ int scot_cpb_bwd_launch(const ScotCpbTable* tab, const float* params, float* gra
   return 0;
 }
 
-// SCOT_ATTN_TC=0: legacy mma.sync kernels for 16 x 16 windows as well (bring-up A/B)
-static bool attn_tc_enabled() {
-  const char* e = getenv("SCOT_ATTN_TC");
-  return !(e != nullptr && e[0] == '0');
-}
-
 #define ATTN_DISPATCH(WS_, HD_, CALL)                                                   \
   if (ws == WS_ && hd == HD_) { return CALL; }
 
@@ -1138,12 +1118,10 @@ int scot_attn_fwd_launch(const void* qkv, void* out, float* lse, const float* ta
   SCOT_REQUIRE(res % ws == 0 && (shift == 0 || shift == ws / 2), "attn_fwd: bad geometry res=%d ws=%d shift=%d", res, ws, shift);
   if (const size_t lo = scot_split_off())  // "parity" precision: fp32 attention on the split-bf16 tensors
     return scot_attn32_fwd_launch(qkv, out, lse, tab2, alpha, batch, res, ws, shift, heads, hd, lo, st);
-  if (ws == 16 && attn_tc_enabled()) return scot_attn_tc_fwd_launch(qkv, out, lse, tab2, alpha, batch, res, shift, heads, hd, st);
+  // 16 x 16 windows (stages 0 and 1 of every shipped model): tcgen05 / TMEM / TMA kernels (attention_tc.cu)
+  if (ws == 16) return scot_attn_tc_fwd_launch(qkv, out, lse, tab2, alpha, batch, res, shift, heads, hd, st);
   WinGeom g{res, shift, res / ws, heads, heads * hd};
   const int tw = batch * g.nws * g.nws;
-  ATTN_DISPATCH(16, 16, (launch_fwd<16, 16>(qkv, out, lse, tab2, alpha, g, tw, st)))
-  ATTN_DISPATCH(16, 32, (launch_fwd<16, 32>(qkv, out, lse, tab2, alpha, g, tw, st)))
-  ATTN_DISPATCH(16, 64, (launch_fwd<16, 64>(qkv, out, lse, tab2, alpha, g, tw, st)))
   ATTN_DISPATCH(8, 16, (launch_fwd<8, 16>(qkv, out, lse, tab2, alpha, g, tw, st)))
   ATTN_DISPATCH(8, 32, (launch_fwd<8, 32>(qkv, out, lse, tab2, alpha, g, tw, st)))
   ATTN_DISPATCH(8, 64, (launch_fwd<8, 64>(qkv, out, lse, tab2, alpha, g, tw, st)))
@@ -1170,7 +1148,8 @@ int scot_attn_bwd_launch2(const void* qkv, const void* o, const void* d_o, const
   if (const size_t lo = scot_split_off())
     return scot_attn32_bwd_launch(qkv, o, d_o, lse, tab2, alpha, dqkv, dtab, dalpha, g_qbias, g_vbias, batch, res, ws, shift,
                                   heads, hd, lo, st);
-  if (ws == 16 && attn_tc_enabled()) {
+  if (ws == 16) {
+    // tcgen05 backward; head_dim 64 (4 x 32 KB of operand tiles beside the staging tiles) stays on the mma.sync kernels
     const int rc = scot_attn_tc_bwd_launch(qkv, o, d_o, lse, tab2, alpha, dqkv, dtab, dalpha, g_qbias, g_vbias, batch, res, shift,
                                            heads, hd, st);
     if (rc != -1) return rc;
@@ -1178,8 +1157,6 @@ int scot_attn_bwd_launch2(const void* qkv, const void* o, const void* d_o, const
   WinGeom g{res, shift, res / ws, heads, heads * hd};
   const int tw = batch * g.nws * g.nws;
 #define BWD_ARGS qkv, o, d_o, lse, tab2, alpha, dqkv, partial, partial_bytes, dtab, dalpha, g_qbias, g_vbias, g, tw, st, fk
-  ATTN_DISPATCH(16, 16, (launch_bwd<16, 16, 8>(BWD_ARGS)))
-  ATTN_DISPATCH(16, 32, (launch_bwd<16, 32, 8>(BWD_ARGS)))
   ATTN_DISPATCH(16, 64, (launch_bwd<16, 64, 4>(BWD_ARGS)))
   ATTN_DISPATCH(8, 16, (launch_bwd<8, 16, 8>(BWD_ARGS)))
   ATTN_DISPATCH(8, 32, (launch_bwd<8, 32, 8>(BWD_ARGS)))

@@ -694,6 +694,176 @@ int shift_of(const Geo& g, int orig_index) { return (orig_index % 2 == 0) ? 0 : 
 
 }  // namespace
 
+
+// ===================================================================================================
+// Stand-alone ScOTLayer entry points: one transformer block through the same block_fwd /
+// block_bwd sequencers the whole-model engine uses. The caller's workspace holds, in this order: a flat fp32 copy of the
+// layer's parameters (engine layout), the flat gradient buffer, and the block's arena (bf16 weights, saved activations,
+// scratch). Parameter order of `params` / `grads` = the reference's state_dict order of a layer:
+//   attention.self.{logit_scale, continuous_position_bias_mlp.0.weight, .0.bias, .2.weight, query.weight, query.bias,
+//   key.weight, value.weight, value.bias}, attention.output.dense.{weight, bias}, layernorm_before.*, intermediate.dense.
+//   {weight, bias}, output.dense.{weight, bias}, layernorm_after.*   (norms: 4 tensors conditioned, 2 otherwise)
+// ===================================================================================================
+namespace {
+
+struct LayerPlan {
+  ScotEngine e;            // host-side plan only (ns = 1, one block)
+  std::vector<long> poff;  // flat offsets of the caller's tensors, in `params` order
+  std::vector<long> pnum;
+  size_t off_params, off_grads, off_arena, off_xb, off_gr, total;
+};
+
+int make_layer_plan(const ScotLayerDesc& L, LayerPlan& P) {
+  SCOT_REQUIRE(L.batch > 0 && L.res > 0 && L.C > 0 && L.heads > 0 && L.C % L.heads == 0, "layer: bad descriptor");
+  SCOT_REQUIRE(L.res % L.window == 0 && (L.shift == 0 || L.shift == L.window / 2), "layer: window %d / shift %d do not fit res %d",
+               L.window, L.shift, L.res);
+  ScotEngine& e = P.e;
+  memset(&e.d, 0, sizeof(e.d));
+  e.d.num_stages = 1;
+  e.d.mlp_ratio = L.mlp_ratio;
+  e.d.use_conditioning = L.use_conditioning;
+  e.d.layer_norm_eps = L.layer_norm_eps;
+  e.d.window_size = L.window;
+  e.d.precision = L.precision;
+  e.batch = L.batch;
+  e.ns = 1;
+  Geo g;
+  g.res = L.res; g.C = L.C; g.heads = L.heads; g.hd = L.C / L.heads; g.ws = L.window; g.shift = L.shift; g.depth = 1;
+  g.M = (long)L.batch * L.res * L.res;
+  SCOT_REQUIRE((g.ws == 16 || g.ws == 8 || g.ws == 4) && (g.hd == 16 || g.hd == 32 || g.hd == 64) && g.C % 16 == 0 &&
+               (long)(L.mlp_ratio * g.C) % 16 == 0, "layer: unsupported window %d / head_dim %d", g.ws, g.hd);
+  e.geo.assign(1, g);
+  Registry R{&e};
+  e.enc.assign(1, std::vector<BlockP>());
+  e.enc[0].push_back(R.block("layer", g.C, g.heads, hidden_of(&e, g.C), L.use_conditioning != 0));
+  e.n_elems = align_up(R.cursor, 64);
+  // `params` order = registration order, except that the Registry registers q/k/v weights and q/v biases separately
+  // already in state_dict order: logit_scale, cpb.0.weight, cpb.0.bias, cpb.2.weight, q.w, k.w, v.w, q.b, v.b, ...
+  // -> map to the documented order (q.w, q.b, k.w, v.w, v.b)
+  std::vector<int> order;
+  for (size_t i = 0; i < e.params.size(); ++i) order.push_back((int)i);
+  // registered: 0 ls, 1 cpb0.w, 2 cpb0.b, 3 cpb2.w, 4 q.w, 5 k.w, 6 v.w, 7 q.b, 8 v.b, 9.. rest in state_dict order
+  const int fix[9] = {0, 1, 2, 3, 4, 7, 5, 6, 8};
+  for (int i = 0; i < 9; ++i) order[i] = fix[i];
+  for (int i : order) {
+    P.poff.push_back(e.params[i].offset);
+    P.pnum.push_back(e.params[i].numel);
+  }
+  Bump b;
+  P.off_params = b.take((size_t)e.n_elems * 4);
+  P.off_grads = b.take((size_t)e.n_elems * 4);
+  P.off_arena = b.off;
+  // arena of the block (offsets relative to off_arena; the split-bf16 shadow doubles it)
+  Bump a;
+  e.wb16 = a.take((size_t)e.n_elems * 2);
+  e.ebuf.assign(1, std::vector<BlockBuf>(1));
+  BlockBuf& bb = e.ebuf[0][0];
+  plan_block(&e, a, bb, g);
+  const size_t M = (size_t)g.M, C = (size_t)g.C, H = (size_t)hidden_of(&e, g.C);
+  e.z32 = a.take(M * C * 4);
+  e.y32 = a.take(M * C * 4);
+  e.dzb = a.take(M * C * 2);
+  e.dzb2 = a.take(M * C * 2);
+  e.dqkv = a.take(M * 3 * C * 2);
+  e.dh = a.take(M * H * 2);
+  e.dob = a.take(M * C * 2);
+  e.partial_bytes = 256;
+  e.partial = a.take(256);
+  const size_t tabn = (size_t)(2 * g.ws - 1) * (2 * g.ws - 1) * g.heads;
+  bb.dtab = a.take(tabn * 4);
+  bb.dalpha = a.take((size_t)g.heads * 4);
+  bb.dpre = a.take(tabn * 4);
+  P.off_xb = a.take(M * C * 2);  // bf16 copy of the layer input
+  P.off_gr = a.take(M * C * 4);
+  e.split_off = 0;
+  size_t arena_bytes = a.off;
+  if (L.precision == 1) {
+    e.split_off = (a.off + 255) & ~size_t(255);
+    arena_bytes = 2 * e.split_off;
+  }
+  ScotCpbTable t;
+  memset(&t, 0, sizeof(t));
+  t.n = 1;
+  const BlockP& p = e.enc[0][0];
+  ScotCpbLayer& cl = t.layer[0];
+  cl.w1 = (int)p.cw1; cl.b1 = (int)p.cb1; cl.w2 = (int)p.cw2; cl.ls = (int)p.ls;
+  cl.tab2 = (int)(bb.tab2 / 256); cl.alpha = (int)(bb.alpha / 256);
+  cl.dtab = (int)(bb.dtab / 256); cl.dalpha = (int)(bb.dalpha / 256); cl.dpre = (int)(bb.dpre / 256);
+  cl.ws = (short)g.ws; cl.heads = (short)g.heads;
+  e.cpb_early.assign(1, t);
+  P.total = P.off_arena + arena_bytes;
+  e.overlap = 0;  // stand-alone layer: everything on the caller's stream
+  e.attn_split_ws = 0;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int scot_layer_num_params(const ScotLayerDesc* L) { return L == nullptr ? 0 : (L->use_conditioning ? 23 : 19); }
+
+size_t scot_layer_workspace_bytes(const ScotLayerDesc* L) {
+  if (L == nullptr) return 0;
+  LayerPlan P;
+  if (make_layer_plan(*L, P) != 0) return 0;
+  return P.total + 256;
+}
+
+int scot_layer_fwd(const ScotLayerDesc* L, const void* const* params, const float* x, const float* time, float* y,
+                   void* workspace, size_t ws_bytes, void* stream) {
+  SCOT_REQUIRE(L && params && x && y && workspace, "layer_fwd: null pointer");
+  SCOT_REQUIRE(!L->use_conditioning || time != nullptr, "layer_fwd: time is required when use_conditioning=True");
+  LayerPlan P;
+  RC(make_layer_plan(*L, P));
+  SCOT_REQUIRE(ws_bytes >= P.total && ((uintptr_t)workspace & 255) == 0, "layer_fwd: workspace too small (%zu < %zu) or not 256 B aligned",
+               ws_bytes, P.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  float* flat = reinterpret_cast<float*>(ws + P.off_params);
+  SCOT_CHECK_CUDA(cudaMemsetAsync(flat, 0, (size_t)P.e.n_elems * 4, st));  // the key-bias slot between q and v biases stays 0
+  for (size_t i = 0; i < P.poff.size(); ++i)
+    SCOT_CHECK_CUDA(cudaMemcpyAsync(flat + P.poff[i], params[i], (size_t)P.pnum[i] * 4, cudaMemcpyDeviceToDevice, st));
+  Ctx c{&P.e, flat, nullptr, ws + P.off_arena, time, st, SCOT_GEMM_TCGEN05};
+  SplitGuard split_guard(P.e.split_off);
+  const Geo& g = P.e.geo[0];
+  RC(scot_cast_f32_bf16_launch(flat, c.at<bf16>(P.e.wb16), P.e.n_elems, st));
+  RC(scot_cpb_fwd_launch(&P.e.cpb_early[0], flat, ws + P.off_arena, st));
+  RC(scot_cast_f32_bf16_launch(x, c.at<bf16>(P.off_xb), g.M * g.C, st));
+  RC(block_fwd(c, P.e.enc[0][0], P.e.ebuf[0][0], g, g.shift, x, c.at<bf16>(P.off_xb)));
+  SCOT_CHECK_CUDA(cudaMemcpyAsync(y, c.at<float>(P.e.ebuf[0][0].xout), (size_t)g.M * g.C * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int scot_layer_bwd(const ScotLayerDesc* L, void* const* grads, const float* time, const float* dy, float* dx, void* workspace,
+                   size_t ws_bytes, void* stream) {
+  SCOT_REQUIRE(L && grads && dy && dx && workspace, "layer_bwd: null pointer");
+  LayerPlan P;
+  RC(make_layer_plan(*L, P));
+  SCOT_REQUIRE(ws_bytes >= P.total && ((uintptr_t)workspace & 255) == 0, "layer_bwd: workspace too small or not 256 B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  float* flat = reinterpret_cast<float*>(ws + P.off_params);   // parameters as left by scot_layer_fwd
+  float* gflat = reinterpret_cast<float*>(ws + P.off_grads);
+  Ctx c{&P.e, flat, gflat, ws + P.off_arena, time, st, SCOT_GEMM_TCGEN05};
+  SplitGuard split_guard(P.e.split_off);
+  const Geo& g = P.e.geo[0];
+  const BlockBuf& bb = P.e.ebuf[0][0];
+  SCOT_CHECK_CUDA(cudaMemsetAsync(gflat, 0, (size_t)P.e.n_elems * 4, st));
+  SCOT_CHECK_CUDA(cudaMemsetAsync(c.at<uint8_t>(bb.dtab), 0, (bb.dpre - bb.dtab), st));
+  float* gr = c.at<float>(P.off_gr);
+  SCOT_CHECK_CUDA(cudaMemcpyAsync(gr, dy, (size_t)g.M * g.C * 4, cudaMemcpyDeviceToDevice, st));
+  RC(block_bwd(c, P.e.enc[0][0], bb, g, g.shift, gr, c.at<bf16>(P.off_xb), 0));
+  RC(scot_cpb_bwd_launch(&P.e.cpb_early[0], flat, gflat, ws + P.off_arena, st));
+  SCOT_CHECK_CUDA(cudaMemcpyAsync(dx, gr, (size_t)g.M * g.C * 4, cudaMemcpyDeviceToDevice, st));
+  for (size_t i = 0; i < P.poff.size(); ++i)
+    if (grads[i] != nullptr)
+      SCOT_CHECK_CUDA(cudaMemcpyAsync(grads[i], gflat + P.poff[i], (size_t)P.pnum[i] * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+}  // extern "C"
+
 // ===================================================================================================
 // C ABI
 // ===================================================================================================

@@ -1,7 +1,7 @@
 """Times the window-attention kernels at the Poseidon-B batch-64 stage shapes (CUDA events, L2 larger than the tensors is
 not flushed: the qkv tensor alone is 37 MB at stage 0, results are for shares / A-B only).
     python scripts/attn_bench.py [fwd|bwd|both]
-SCOT_ATTN_TC=0 selects the legacy mma.sync kernels for 16 x 16 windows."""
+"""
 import json
 import math
 import os

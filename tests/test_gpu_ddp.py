@@ -88,8 +88,8 @@ def test_split_backward_equals_whole_backward():
     from poseidon_b200.scOT.model import ScOT, ScOTConfig
 
     dev = torch.device("cuda", 0)
-    cfg = dict(CFG, depths=[2, 2, 2], num_heads=[2, 4, 8], skip_connections=[1, 1, 0])
-    x, t, y, _ = make_inputs(4, 2, 2, 32, seed=3)
+    cfg = dict(CFG, image_size=64, depths=[2, 2, 2], num_heads=[2, 4, 8], skip_connections=[1, 1, 0])
+    x, t, y, _ = make_inputs(4, 2, 2, 64, seed=3)
     grads = {}
     for mode in ("whole", "split"):
         model = ScOT(ScOTConfig(**cfg))

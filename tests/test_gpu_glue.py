@@ -234,3 +234,53 @@ def test_standalone_conditional_layer_norm_module():
     assert rel(x.grad, gx) < 6e-3 and rel(m.weight.weight.grad, gw) < 6e-3  # zhat is saved in bf16
     with pytest.raises(RuntimeError):
         m.cpu()(x.detach().cpu(), t.cpu())
+
+
+LAYER_KEYS = ["attention.self.logit_scale", "attention.self.continuous_position_bias_mlp.0.weight",
+              "attention.self.continuous_position_bias_mlp.0.bias", "attention.self.continuous_position_bias_mlp.2.weight",
+              "attention.self.query.weight", "attention.self.query.bias", "attention.self.key.weight",
+              "attention.self.value.weight", "attention.self.value.bias", "attention.output.dense.weight",
+              "attention.output.dense.bias", "layernorm_before.weight.weight", "layernorm_before.weight.bias",
+              "layernorm_before.bias.weight", "layernorm_before.bias.bias", "intermediate.dense.weight",
+              "intermediate.dense.bias", "output.dense.weight", "output.dense.bias", "layernorm_after.weight.weight",
+              "layernorm_after.weight.bias", "layernorm_after.bias.weight", "layernorm_after.bias.bias"]
+
+
+@pytest.mark.parametrize("geom", [(2, 32, 96, 3, 16, 8), (3, 16, 64, 4, 8, 0), (2, 8, 64, 2, 4, 2)])
+def test_standalone_layer_forward_backward(L, geom):
+    """scot_layer_fwd / scot_layer_bwd (one ScOTLayer, scOT/model.py:500-581) against the fp64 oracle layer, parity precision"""
+    from oracle.weights import make_weight
+
+    Bn, res, C, heads, ws, shift = geom
+    hidden = 4 * C
+    shapes = {"attention.self.logit_scale": (heads, 1, 1), "attention.self.continuous_position_bias_mlp.0.weight": (512, 2),
+              "attention.self.continuous_position_bias_mlp.0.bias": (512,),
+              "attention.self.continuous_position_bias_mlp.2.weight": (heads, 512), "attention.self.query.weight": (C, C),
+              "attention.self.query.bias": (C,), "attention.self.key.weight": (C, C), "attention.self.value.weight": (C, C),
+              "attention.self.value.bias": (C,), "attention.output.dense.weight": (C, C), "attention.output.dense.bias": (C,),
+              "intermediate.dense.weight": (hidden, C), "intermediate.dense.bias": (hidden,), "output.dense.weight": (C, hidden),
+              "output.dense.bias": (C,)}
+    for n in ("layernorm_before", "layernorm_after"):
+        shapes.update({f"{n}.weight.weight": (C, 1), f"{n}.weight.bias": (C,), f"{n}.bias.weight": (C, 1), f"{n}.bias.bias": (C,)})
+    assert len(LAYER_KEYS) == 23
+    keys = LAYER_KEYS[:11] + LAYER_KEYS[11:15] + LAYER_KEYS[15:19] + LAYER_KEYS[19:]
+    w = {"blk." + k: make_weight("encoder.layers.0.blocks.0." + k, shapes[k], seed=5) for k in keys}
+    params = [w["blk." + k].to(dev).contiguous() for k in keys]
+    lay = L.Layer(Bn, res, C, heads, ws, shift, 4.0, True, 1e-5, precision=1)
+    assert lay.n == 23  # 9 attention.self + 2 attention.output + 4 + 2 + 2 + 4 tensors
+    torch.manual_seed(1)
+    x = torch.randn(Bn * res * res, C, device=dev)
+    t = torch.rand(Bn, device=dev)
+    y = lay.forward(params, x, t)
+    wd = {k: v.double().to(dev).requires_grad_(True) for k, v in w.items()}
+    xd = x.double().view(Bn, res * res, C).requires_grad_(True)
+    ref = O.scot_layer(xd, t.double(), wd, "blk", dict(res=res, ws=ws, heads=heads), shift, 1e-5, True)
+    assert rel(y, ref.reshape(-1, C)) < 1e-4
+    dy = torch.randn_like(y)
+    ref.backward(dy.double().view_as(ref))
+    grads = [torch.zeros_like(p) for p in params]
+    dx = lay.backward(grads, t, dy)
+    assert rel(dx, xd.grad.reshape(-1, C)) < 1e-3
+    for k, g in zip(keys, grads):
+        r = rel(g, wd["blk." + k].grad)
+        assert r < 5e-3, (k, r)
