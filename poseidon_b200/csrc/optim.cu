@@ -17,6 +17,13 @@
 
 namespace {
 
+// Deterministic: per-block partial sums land in a fixed scratch slot and the LAST block to finish adds them in block order,
+// so every data-parallel rank computes bit-identical norms (an atomicAdd of the partials rounds differently from run to run
+// and from rank to rank: the clip coefficient, and with it the replicas, would drift apart in the last bit).
+constexpr int kNormMaxBlocks = 2048;
+__device__ float g_norm_partials[kNormMaxBlocks];
+__device__ unsigned int g_norm_count = 0;
+
 __global__ void __launch_bounds__(256) grad_sq_norm_kernel(const float* __restrict__ g, long n4, float* __restrict__ out) {
   float acc = 0.f;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
@@ -25,14 +32,23 @@ __global__ void __launch_bounds__(256) grad_sq_norm_kernel(const float* __restri
   }
   acc = warp_sum(acc);
   __shared__ float s[8];
+  __shared__ bool last;
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x < 8) {
-    float v = s[threadIdx.x];
-    v += __shfl_xor_sync(0xffu, v, 4);
-    v += __shfl_xor_sync(0xffu, v, 2);
-    v += __shfl_xor_sync(0xffu, v, 1);
-    if (threadIdx.x == 0) atomicAdd(out, v);
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int k = 0; k < 8; ++k) v += s[k];
+    g_norm_partials[blockIdx.x] = v;
+    __threadfence();
+    last = (atomicAdd(&g_norm_count, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float total = 0.f;
+    for (unsigned k = 0; k < gridDim.x; ++k) total += reinterpret_cast<volatile float*>(g_norm_partials)[k];
+    out[0] = total;
+    g_norm_count = 0;  // ready for the next launch (launches of this kernel are stream-ordered)
   }
 }
 
@@ -93,7 +109,9 @@ int scot_grad_sq_norm(const float* grads, long n_elems, float* out, void* stream
   SCOT_REQUIRE(grads && out && n_elems > 0 && n_elems % 4 == 0, "grad_sq_norm: bad arguments (n must be a multiple of 4)");
   cudaStream_t st = (cudaStream_t)stream;
   SCOT_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
-  grad_sq_norm_kernel<<<grid_for(n_elems / 4), 256, 0, st>>>(grads, n_elems / 4, out);
+  int grid = grid_for(n_elems / 4);
+  if (grid > kNormMaxBlocks) grid = kNormMaxBlocks;
+  grad_sq_norm_kernel<<<grid, 256, 0, st>>>(grads, n_elems / 4, out);
   SCOT_LAUNCH_CHECK();
   return 0;
 }
