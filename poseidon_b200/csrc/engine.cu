@@ -496,23 +496,86 @@ int norm_bwd(const Ctx& c, const NormP& n, const float* dy, const void* zhat, co
 // ---------------------------------------------------------------------------------------------------
 // ScOTLayer forward / backward (scOT/model.py:500-581)
 // ---------------------------------------------------------------------------------------------------
+// A block can run on a SAMPLE RANGE of the batch (token-major layouts: a range of samples is a contiguous range of rows of
+// every per-token tensor): `BlkView` holds the block's buffers shifted to the first row of the range. (Round 2 measured two
+// half-batch chains on two streams at the deep stages: 20.63 ms vs 20.15 ms per Poseidon-B step — slower, dropped; the
+// engine and the stand-alone layer entry points run whole-batch views.)
+struct BlkView {
+  bf16 *qkv, *o;
+  float* lse;
+  bf16 *zhat1, *y1b, *h, *gl, *zhat2, *xbout;
+  float *rstd1, *rstd2, *xout;
+  float *tab2, *alpha, *dtab, *dalpha;
+  float *z32, *y32;                         // fp32 scratch
+  bf16 *dzb, *dzb2, *dh, *dob, *dqkv;       // backward scratch
+  const float* time;                        // lead times of the range
+  long M;                                   // rows of the range
+  int batch;                                // samples of the range
+};
+
+BlkView view_of(const Ctx& c, const BlockBuf& b, const Geo& g, int sample0, int nsamples, int set) {
+  const ScotEngine* e = c.e;
+  const long r0 = (long)sample0 * g.res * g.res, C = g.C, H = hidden_of(e, g.C);
+  BlkView v;
+  v.qkv = c.at<bf16>(b.qkv) + r0 * 3 * C;
+  v.o = c.at<bf16>(b.o) + r0 * C;
+  v.lse = c.at<float>(b.lse) + r0 * g.heads;  // units * N = samples * res^2 * heads
+  v.zhat1 = c.at<bf16>(b.zhat1) + r0 * C;
+  v.rstd1 = c.at<float>(b.rstd1) + r0;
+  v.y1b = c.at<bf16>(b.y1b) + r0 * C;
+  v.h = c.at<bf16>(b.h) + r0 * H;
+  v.gl = c.at<bf16>(b.g) + r0 * H;
+  v.zhat2 = c.at<bf16>(b.zhat2) + r0 * C;
+  v.rstd2 = c.at<float>(b.rstd2) + r0;
+  v.xout = c.at<float>(b.xout) + r0 * C;
+  v.xbout = c.at<bf16>(b.xbout) + r0 * C;
+  v.tab2 = c.at<float>(b.tab2);
+  v.alpha = c.at<float>(b.alpha);
+  v.dtab = c.at<float>(b.dtab);
+  v.dalpha = c.at<float>(b.dalpha);
+  v.z32 = c.at<float>(e->z32) + r0 * C;
+  v.y32 = c.at<float>(e->y32) + r0 * C;
+  v.dzb = c.at<bf16>(set ? e->dzbB : e->dzb) + r0 * C;
+  v.dzb2 = c.at<bf16>(set ? e->dzb2B : e->dzb2) + r0 * C;
+  v.dh = c.at<bf16>(set ? e->dhB : e->dh) + r0 * H;
+  v.dob = c.at<bf16>(set ? e->dobB : e->dob) + r0 * C;
+  v.dqkv = c.at<bf16>(set ? e->dqkvB : e->dqkv) + r0 * 3 * C;
+  v.time = c.time != nullptr ? c.time + sample0 : nullptr;
+  v.M = (long)nsamples * g.res * g.res;
+  v.batch = nsamples;
+  return v;
+}
+
+int norm_fwd_t(const Ctx& c, const NormP& n, const float* time, const float* z, const float* residual, float* x_out, void* xb_out,
+               void* zhat, float* rstd, long rows, int C, int rows_per_sample, float eps) {
+  return scot_cln_fwd_launch(z, residual, n.ww >= 0 ? time : nullptr, c.p(n.ww), c.p(n.wb), c.p(n.bw), c.p(n.bb), x_out, xb_out,
+                             zhat, rstd, rows, C, rows_per_sample, 0, eps, c.st);
+}
+int norm_bwd_t(const Ctx& c, const NormP& n, const float* time, const float* dy, const void* zhat, const float* rstd, void* dz,
+               float* g_bias_prev, long rows, int C, int rows_per_sample) {
+  return scot_cln_bwd_launch(dy, zhat, rstd, n.ww >= 0 ? time : nullptr, c.p(n.ww), c.p(n.wb), dz, 0, c.g(n.ww), c.g(n.wb),
+                             c.g(n.bw), c.g(n.bb), g_bias_prev, rows, C, rows_per_sample, 0, c.st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ScOTLayer forward / backward (scOT/model.py:500-581) on the rows of `v`; everything is enqueued on c.st
+// ---------------------------------------------------------------------------------------------------
+int block_fwd_v(const Ctx& c, const BlockP& p, const BlkView& v, const Geo& g, int shift, const float* x_in, const bf16* xb_in) {
+  const ScotEngine* e = c.e;
+  const long M = v.M, C = g.C, H = hidden_of(e, g.C);
+  const int T = g.res * g.res;
+  RC(gemm(c, xb_in, C, 0, c.w16(p.wqkv), C, 0, M, 3 * C, C, SCOT_EPI_BF16, c.p(p.bqkv), v.qkv, 3 * C));
+  RC(scot_attn_fwd_launch(v.qkv, v.o, v.lse, v.tab2, v.alpha, v.batch, g.res, g.ws, shift, g.heads, g.hd, c.st));
+  RC(gemm(c, v.o, C, 0, c.w16(p.wo), C, 0, M, C, C, SCOT_EPI_F32, c.p(p.bo), v.z32, C));
+  RC(norm_fwd_t(c, p.ln1, v.time, v.z32, x_in, v.y32, v.y1b, v.zhat1, v.rstd1, M, (int)C, T, e->d.layer_norm_eps));
+  RC(gemm(c, v.y1b, C, 0, c.w16(p.w1), C, 0, M, H, C, SCOT_EPI_GELU, c.p(p.b1), v.h, H, v.gl, H));
+  RC(gemm(c, v.gl, H, 0, c.w16(p.w2), H, 0, M, C, H, SCOT_EPI_F32, c.p(p.b2), v.z32, C));
+  RC(norm_fwd_t(c, p.ln2, v.time, v.z32, v.y32, v.xout, v.xbout, v.zhat2, v.rstd2, M, (int)C, T, e->d.layer_norm_eps));
+  return 0;
+}
 int block_fwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, int shift, const float* x_in,
               const bf16* xb_in) {
-  const ScotEngine* e = c.e;
-  const long M = g.M, C = g.C, H = hidden_of(e, g.C);
-  const int T = g.res * g.res;
-  RC(gemm(c, xb_in, C, 0, c.w16(p.wqkv), C, 0, M, 3 * C, C, SCOT_EPI_BF16, c.p(p.bqkv), c.at<bf16>(b.qkv), 3 * C));
-  RC(scot_attn_fwd_launch(c.at<bf16>(b.qkv), c.at<bf16>(b.o), c.at<float>(b.lse), c.at<float>(b.tab2), c.at<float>(b.alpha),
-                          e->batch, g.res, g.ws, shift, g.heads, g.hd, c.st));
-  RC(gemm(c, c.at<bf16>(b.o), C, 0, c.w16(p.wo), C, 0, M, C, C, SCOT_EPI_F32, c.p(p.bo), c.at<float>(e->z32), C));
-  RC(norm_fwd(c, p.ln1, c.at<float>(e->z32), x_in, c.at<float>(e->y32), c.at<bf16>(b.y1b), c.at<bf16>(b.zhat1),
-              c.at<float>(b.rstd1), M, (int)C, T, 0, e->d.layer_norm_eps));
-  RC(gemm(c, c.at<bf16>(b.y1b), C, 0, c.w16(p.w1), C, 0, M, H, C, SCOT_EPI_GELU, c.p(p.b1), c.at<bf16>(b.h), H,
-          c.at<bf16>(b.g), H));
-  RC(gemm(c, c.at<bf16>(b.g), H, 0, c.w16(p.w2), H, 0, M, C, H, SCOT_EPI_F32, c.p(p.b2), c.at<float>(e->z32), C));
-  RC(norm_fwd(c, p.ln2, c.at<float>(e->z32), c.at<float>(e->y32), c.at<float>(b.xout), c.at<bf16>(b.xbout),
-              c.at<bf16>(b.zhat2), c.at<float>(b.rstd2), M, (int)C, T, 0, e->d.layer_norm_eps));
-  return 0;
+  return block_fwd_v(c, p, view_of(c, b, g, 0, c.e->batch, 0), g, shift, x_in, xb_in);
 }
 
 // main stream waits until the side-stream work that used scratch set `set` has finished
@@ -530,54 +593,51 @@ int join_all(const Ctx& c) {
   return 0;
 }
 
-// g: gradient wrt the block output on entry, wrt the block input on exit (fp32, in place).
-// The four weight-gradient GEMMs are side branches of the chain: their operands stay alive until the end of the block
-// (separate dz buffers for the two norms), so they are issued as ONE grouped launch after the data-gradient chain — on
-// a second stream: consecutive blocks alternate between two sets of scratch buffers (`set`), so the weight gradients
-// of block i run concurrently with the data-gradient chain of block i-1 (fork / join through events; the pattern is
-// captured into the CUDA graph as parallel branches). At the deep stages both are small, latency-bound kernels.
-int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, int shift, float* gr, const bf16* xb_in, int set) {
+// gr: gradient wrt the block output on entry, wrt the block input on exit (fp32, in place; rows of `v`).
+// side_ok: the four weight-gradient GEMMs may go to the side stream (full-batch path): their operands stay alive until the
+// end of the block (separate dz buffers for the two norms), consecutive blocks alternate between two sets of scratch buffers
+// (`set`), so the weight gradients of block i run concurrently with the data-gradient chain of block i-1 (fork / join through
+// events, captured into the CUDA graph as parallel branches). Sample-range calls (side_ok = false) run everything in line on
+// c.st: their concurrency comes from the other half of the batch.
+int block_bwd_v(const Ctx& c, const BlockP& p, const BlkView& v, const Geo& g, int shift, float* gr, const bf16* xb_in, int set,
+                bool side_ok) {
   ScotEngine* e = c.e;
-  const long M = g.M, C = g.C, H = hidden_of(e, g.C);
+  const long M = v.M, C = g.C, H = hidden_of(e, g.C);
   const int T = g.res * g.res;
-  RC(join_side(c, set));  // the weight gradients issued two blocks ago read this scratch set
-  bf16* dzb = c.at<bf16>(set ? e->dzbB : e->dzb);
-  bf16* dzb2 = c.at<bf16>(set ? e->dzb2B : e->dzb2);
-  bf16* dh = c.at<bf16>(set ? e->dhB : e->dh);
+  if (side_ok) RC(join_side(c, set));  // the weight gradients issued two blocks ago read this scratch set
   // y = y1 + LN2(mlp(y1))
-  RC(norm_bwd(c, p.ln2, gr, c.at<bf16>(b.zhat2), c.at<float>(b.rstd2), dzb2, 0, c.g(p.b2), M, (int)C, T, 0));
-  RC(gemm(c, dzb2, C, 0, c.w16(p.w2), H, 1, M, H, C, SCOT_EPI_GELU_BWD, nullptr, dh, H, nullptr, 0, c.at<bf16>(b.h), H,
-          c.g(p.b1)));
-  RC(gemm(c, dh, H, 0, c.w16(p.w1), C, 1, M, C, H, SCOT_EPI_RMW_F32, nullptr, gr, C));
+  RC(norm_bwd_t(c, p.ln2, v.time, gr, v.zhat2, v.rstd2, v.dzb2, c.g(p.b2), M, (int)C, T));
+  RC(gemm(c, v.dzb2, C, 0, c.w16(p.w2), H, 1, M, H, C, SCOT_EPI_GELU_BWD, nullptr, v.dh, H, nullptr, 0, v.h, H, c.g(p.b1)));
+  RC(gemm(c, v.dh, H, 0, c.w16(p.w1), C, 1, M, C, H, SCOT_EPI_RMW_F32, nullptr, gr, C));
   // y1 = x + LN1(attn(x))
-  RC(norm_bwd(c, p.ln1, gr, c.at<bf16>(b.zhat1), c.at<float>(b.rstd1), dzb, 0, c.g(p.bo), M, (int)C, T, 0));
-  bf16* dob = c.at<bf16>(set ? e->dobB : e->dob);
-  RC(gemm(c, dzb, C, 0, c.w16(p.wo), C, 1, M, C, C, SCOT_EPI_BF16, nullptr, dob, C));
-  bf16* dqkv = c.at<bf16>(set ? e->dqkvB : e->dqkv);
+  RC(norm_bwd_t(c, p.ln1, v.time, gr, v.zhat1, v.rstd1, v.dzb, c.g(p.bo), M, (int)C, T));
+  RC(gemm(c, v.dzb, C, 0, c.w16(p.wo), C, 1, M, C, C, SCOT_EPI_BF16, nullptr, v.dob, C));
   ScotAttnBwdFork fk{e->side3, e->ev_afork, e->ev_ajoin};
-  const bool fork_attn = e->side3 != nullptr && g.ws <= e->attn_split_ws;
-  RC(scot_attn_bwd_launch2(c.at<bf16>(b.qkv), c.at<bf16>(b.o), dob, c.at<float>(b.lse), c.at<float>(b.tab2),
-                           c.at<float>(b.alpha), dqkv, c.at<float>(e->partial), e->partial_bytes, c.at<float>(b.dtab),
-                           c.at<float>(b.dalpha), c.g(p.bqkv), c.g(p.bqkv + 2 * C), e->batch, g.res, g.ws, shift, g.heads,
-                           g.hd, c.st, fork_attn ? &fk : nullptr));
+  const bool fork_attn = side_ok && e->side3 != nullptr && g.ws <= e->attn_split_ws;
+  RC(scot_attn_bwd_launch2(v.qkv, v.o, v.dob, v.lse, v.tab2, v.alpha, v.dqkv, c.at<float>(e->partial), e->partial_bytes, v.dtab,
+                           v.dalpha, c.g(p.bqkv), c.g(p.bqkv + 2 * C), v.batch, g.res, g.ws, shift, g.heads, g.hd, c.st,
+                           fork_attn ? &fk : nullptr));
   const ScotWgradProblem wg[4] = {
-      {dzb2, C, c.at<bf16>(b.g), H, c.g(p.w2), H, M, (int)C, (int)H},         // output.dense
-      {dh, H, c.at<bf16>(b.y1b), C, c.g(p.w1), C, M, (int)H, (int)C},         // intermediate.dense
-      {dzb, C, c.at<bf16>(b.o), C, c.g(p.wo), C, M, (int)C, (int)C},          // attention.output.dense
-      {dqkv, 3 * C, xb_in, C, c.g(p.wqkv), C, M, (int)(3 * C), (int)C},       // query | key | value
+      {v.dzb2, C, v.gl, H, c.g(p.w2), H, M, (int)C, (int)H},              // output.dense
+      {v.dh, H, v.y1b, C, c.g(p.w1), C, M, (int)H, (int)C},               // intermediate.dense
+      {v.dzb, C, v.o, C, c.g(p.wo), C, M, (int)C, (int)C},                // attention.output.dense
+      {v.dqkv, 3 * C, xb_in, C, c.g(p.wqkv), C, M, (int)(3 * C), (int)C},  // query | key | value
   };
-  if (e->overlap && e->side != nullptr) {
+  if (side_ok && e->overlap && e->side != nullptr) {
     SCOT_CHECK_CUDA(cudaEventRecord(e->ev_fork[set], c.st));  // all four dY operands are complete here
     SCOT_CHECK_CUDA(cudaStreamWaitEvent(e->side, e->ev_fork[set], 0));
     RC(scot_gemm_wgrad_group_launch(wg, 4, c.impl, e->side));
     SCOT_CHECK_CUDA(cudaEventRecord(e->ev_join[set], e->side));
     e->join_pending[set] = true;
-    RC(gemm(c, dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
+    RC(gemm(c, v.dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
   } else {
-    RC(gemm(c, dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
+    RC(gemm(c, v.dqkv, 3 * C, 0, c.w16(p.wqkv), C, 1, M, C, 3 * C, SCOT_EPI_RMW_F32, nullptr, gr, C));
     RC(scot_gemm_wgrad_group_launch(wg, 4, c.impl, c.st));
   }
   return 0;
+}
+int block_bwd(const Ctx& c, const BlockP& p, const BlockBuf& b, const Geo& g, int shift, float* gr, const bf16* xb_in, int set) {
+  return block_bwd_v(c, p, view_of(c, b, g, 0, c.e->batch, set), g, shift, gr, xb_in, set, true);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -19,19 +19,13 @@ from bench import model_config, realistic_init_  # noqa: E402
 from poseidon_b200.runtime import GraphedTrainStep  # noqa: E402
 from poseidon_b200.scOT.model import ScOT, ScOTConfig  # noqa: E402
 
-OFF = {"SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "16", "SCOT_GEMM_ASYNC_V2": "0", "SCOT_ATTN_DQ_FOLD2": "0"}
+OFF = {"SCOT_CNX_OVERLAP": "1", "SCOT_ATTN_BWD_SPLIT": "16"}
 SETTINGS = [
     ("defaults", {}),  # must stay first: the reference everything else is compared with
     ("inline", {"SCOT_CNX_OVERLAP": "0", "SCOT_ATTN_BWD_SPLIT": "0"}),
     ("cnx_only", {"SCOT_ATTN_BWD_SPLIT": "0"}),
     ("attn_only", {"SCOT_CNX_OVERLAP": "0"}),
     # round-2 candidates (never run on hardware when this was written): run them one per process under a timeout,
-    # e.g.  timeout 120 python scripts/ab_overlap.py B 64 20 defaults,gemm_v2
-    ("gemm_v2", {"SCOT_GEMM_ASYNC_V2": "1"}),
-    ("gemm_v2_2g", {"SCOT_GEMM_ASYNC_V2": "3"}),
-    ("gemm_v2_smallk", {"SCOT_GEMM_ASYNC_V2": "5"}),
-    ("gemm_v2_all", {"SCOT_GEMM_ASYNC_V2": "7"}),
-    ("dq_fold2", {"SCOT_ATTN_DQ_FOLD2": "1"}),
 ]
 DEFAULT_RUN = ("defaults", "inline", "cnx_only", "attn_only")
 

@@ -25,3 +25,10 @@ for i in range(nsteps):
     step.run()
     torch.cuda.synchronize()
     print("step", i, "launches", lib.scot_launch_count() - c0, "loss", float(step.loss))
+
+if len(sys.argv) > 4 and sys.argv[4] == "opt":  # one fused clip + AdamW step as well (for the ncu rows of optim.cu)
+    from poseidon_b200.optim import FlatAdamW, build_param_groups
+    opt = FlatAdamW(build_param_groups(model, 0.01), model, lr=1e-6, max_grad_norm=5.0)
+    opt.step()
+    torch.cuda.synchronize()
+    print("optimizer step done")
