@@ -110,6 +110,23 @@ __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
   cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;                  // Phi(x)
   pdf = 0.39894228040143267794f * e2;                             // phi(x)
 }
+// gelu(x) and gelu'(x) together, same erf form as gelu_parts with the constant factors folded (|x|/sqrt2 into the rcp
+// argument, the 1/2 of erfc into the polynomial, phi's 1/sqrt(2 pi) into x): 6 FMUL + 6 FFMA + 2 MUFU + 3 select per
+// element — the GELU GEMM epilogue is issue-bound on exactly this sequence.
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) {
+  float e2;  // exp(-x^2/2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"((x * x) * -0.72134752044448170368f));
+  float t;   // 1/(1 + p|x|/sqrt2)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f)));
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float half_erfc = (poly * t) * e2;                        // (1 - erf(|x|/sqrt 2)) / 2
+  const float cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;      // Phi(x)
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143267794f, e2, cdf);               // Phi(x) + x phi(x)
+}
 // full-precision variant for the split-bf16 ("parity") mode: libm erff / expf (a few ulp)
 __device__ __forceinline__ void gelu_parts_precise(float x, float& cdf, float& pdf) {
   cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));

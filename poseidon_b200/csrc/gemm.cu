@@ -421,7 +421,8 @@ struct AsyncArgs {
 };
 
 constexpr int ABN = 64;                       // tile width of the async-epilogue kernel
-constexpr int kOutTileBytes = BM * ABN * 2;   // one 128 x 64 bf16 tile = 16 KB (128 B rows, 128B swizzle)
+constexpr int kOutTileBytes = BM * ABN * 2;   // one 128 x 64 bf16 tile = 16 KB (aux ring: 128 B rows, 128B swizzle)
+constexpr int kSlabBytes = 32 * 32 * 2;       // output staging slab of one epilogue warp: 32 rows x 64 B (SWIZZLE_64B)
 constexpr int kAStageBytes = BM * BK * 2 + ABN * BK * 2;
 
 template <int BMN, int MODE>
@@ -463,9 +464,9 @@ gemm_async_epi_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], EPI_THREADS);
+      mbar_init(&tmem_empty_bar[b], EPI_THREADS / 32);  // one arrival per epilogue warp
       mbar_init(&aux_full_bar[b], 1);
-      mbar_init(&aux_empty_bar[b], EPI_THREADS);
+      mbar_init(&aux_empty_bar[b], EPI_THREADS / 32);
     }
     mbar_fence_init();
   }
@@ -533,17 +534,21 @@ gemm_async_epi_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
       }
     }
   } else {
-    // ------------------------------ epilogue (8 warps) ------------------------------
+    // ------------------------------ epilogue (8 independent warps) ------------------------------
+    // Warp (q, half) owns the 32 rows x 32 columns of the tile it can read from TMEM and a private 2 KB staging slab per
+    // output: it converts, stages, and bulk-stores its slab on its own (64 B rows, SWIZZLE_64B box), so the eight warps
+    // never meet at a CTA barrier and drift apart — one warp's SFU-heavy conversion overlaps another's TMEM load / store.
     const int ew = warp - 2;             // 0..7
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int half = ew >> 2;            // which 32-column half of the tile this warp converts
-    const int et = ew * 32 + lane;       // 0..255
     const int row = q * 32 + lane;       // accumulator row (TMEM lane) of this thread
-    const bool issuer = (et == 0);       // issues / tracks the bulk stores
-    const uint32_t swz = (uint32_t)(row & 7);
-    const uint32_t out_row = smem_u32(out_s) + (uint32_t)row * 128u;
+    const uint32_t slab0 = smem_u32(out_s) + (uint32_t)ew * kSlabBytes;             // output 0 (or the only one)
+    const uint32_t slab1 = slab0 + 8u * kSlabBytes;                                  // output 1 (GELU)
+    const uint32_t srow = (uint32_t)lane * 64u;                                      // this thread's 64 B row in the slab
+    const uint32_t sswz = (uint32_t)((lane >> 1) & 3);                               // SWIZZLE_64B: chunk ^= (row >> 1) & 3
     const uint32_t aux_row = smem_u32(aux_s) + (uint32_t)row * 128u;
-    float cs0 = 0.f, cs1 = 0.f;          // GELU_BWD: running sums of columns 2*(et&31), +1 over rows (et>>5)*16..+15
+    const uint32_t aswz = (uint32_t)(row & 7);
+    float cs0 = 0.f, cs1 = 0.f;          // GELU_BWD: running column sums (columns 2p, 2p+1 of this warp's half; rows of parity lane>>4)
     float bias[(MODE == SCOT_EPI_GELU_BWD) ? 1 : 32];  // bias of this thread's 32 columns, reloaded per column block
     int bias_cb = -1;
     int lt = 0;
@@ -563,28 +568,27 @@ gemm_async_epi_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
       tc_fence_after();
       float v[32];
       tmem_ld_32x32(tmem_base + (uint32_t)(buf * kAccCols + half * 32) + ((uint32_t)(q * 32) << 16), v);
-      // the previous tile's bulk store must have finished reading the output tile(s) in smem (it had a whole tile time)
-      if (issuer) bulk_wait_read<0>();
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      // the previous tile's bulk store(s) of this warp must have finished reading the slab (they had a whole tile time)
+      if (lane == 0) bulk_wait_read<0>();
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[buf]);  // the MMA warp may start the tile after next in this accumulator
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);  // the MMA warp may start the tile after next in this accumulator
       if constexpr (MODE == SCOT_EPI_GELU) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {  // 8 columns = one 16-byte chunk of each output row
           uint32_t g4[4], a4[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float x0 = v[j * 8 + 2 * k] + bias[j * 8 + 2 * k], x1 = v[j * 8 + 2 * k + 1] + bias[j * 8 + 2 * k + 1];
-            float c0, p0, c1, p1;
-            gelu_parts(x0, c0, p0);
-            gelu_parts(x1, c1, p1);
-            g4[k] = pack_bf16x2(fmaf(x0, p0, c0), fmaf(x1, p1, c1));  // gelu'
-            a4[k] = pack_bf16x2(x0 * c0, x1 * c1);                    // gelu
+            float g0, d0, g1, d1;
+            gelu_and_grad(v[j * 8 + 2 * k] + bias[j * 8 + 2 * k], g0, d0);
+            gelu_and_grad(v[j * 8 + 2 * k + 1] + bias[j * 8 + 2 * k + 1], g1, d1);
+            g4[k] = pack_bf16x2(d0, d1);  // gelu'
+            a4[k] = pack_bf16x2(g0, g1);  // gelu
           }
-          const uint32_t off = (((uint32_t)(half * 4 + j)) ^ swz) << 4;
-          sts128(out_row + off, g4[0], g4[1], g4[2], g4[3]);
-          sts128(out_row + kOutTileBytes + off, a4[0], a4[1], a4[2], a4[3]);
+          const uint32_t off = srow + ((((uint32_t)j) ^ sswz) << 4);
+          sts128(slab0 + off, g4[0], g4[1], g4[2], g4[3]);
+          sts128(slab1 + off, a4[0], a4[1], a4[2], a4[3]);
         }
       } else if constexpr (MODE == SCOT_EPI_BF16) {
 #pragma unroll
@@ -593,15 +597,16 @@ gemm_async_epi_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             o4[k] = pack_bf16x2(v[j * 8 + 2 * k] + bias[j * 8 + 2 * k], v[j * 8 + 2 * k + 1] + bias[j * 8 + 2 * k + 1]);
-          sts128(out_row + ((((uint32_t)(half * 4 + j)) ^ swz) << 4), o4[0], o4[1], o4[2], o4[3]);
+          sts128(slab0 + srow + ((((uint32_t)j) ^ sswz) << 4), o4[0], o4[1], o4[2], o4[3]);
         }
       } else {  // GELU_BWD: dh = acc * gelu'(h), gelu'(h) from the aux ring
         const int as = lt & 1;
         mbar_wait(&aux_full_bar[as], ((uint32_t)lt >> 1) & 1u);
         uint4 a[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a[j] = lds128(aux_row + (uint32_t)(as * kOutTileBytes) + ((((uint32_t)(half * 4 + j)) ^ swz) << 4));
-        mbar_arrive(&aux_empty_bar[as]);
+        for (int j = 0; j < 4; ++j) a[j] = lds128(aux_row + (uint32_t)(as * kOutTileBytes) + ((((uint32_t)(half * 4 + j)) ^ aswz) << 4));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aux_empty_bar[as]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t w[4] = {a[j].x, a[j].y, a[j].z, a[j].w};
@@ -611,42 +616,46 @@ gemm_async_epi_kernel(const __grid_constant__ AsyncArgs ga, int num_stages) {
             const float2 g = unpack_bf16x2(w[k]);
             o4[k] = pack_bf16x2(v[j * 8 + 2 * k] * g.x, v[j * 8 + 2 * k + 1] * g.y);
           }
-          sts128(out_row + ((((uint32_t)(half * 4 + j)) ^ swz) << 4), o4[0], o4[1], o4[2], o4[3]);
+          sts128(slab0 + srow + ((((uint32_t)j) ^ sswz) << 4), o4[0], o4[1], o4[2], o4[3]);
         }
       }
       fence_proxy_async_smem();
-      asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
-      if (issuer) {
+      __syncwarp();
+      const int nc = n0 + half * 32, mr = m0 + q * 32;
+      if (lane == 0 && nc < ga.N && mr < ga.M) {  // the box is clipped at the tensor edges by the TMA unit
         if constexpr (MODE == SCOT_EPI_GELU) {
-          if (ga.has_out0) tma_store_2d(&ga.tmOut0, out_s, n0, m0);
-          tma_store_2d(&ga.tmOut1, out_s + kOutTileBytes, n0, m0);
+          if (ga.has_out0) tma_store_2d(&ga.tmOut0, reinterpret_cast<const void*>(out_s + (size_t)ew * kSlabBytes), nc, mr);
+          tma_store_2d(&ga.tmOut1, reinterpret_cast<const void*>(out_s + (size_t)(8 + ew) * kSlabBytes), nc, mr);
         } else {
-          tma_store_2d(&ga.tmOut0, out_s, n0, m0);
+          tma_store_2d(&ga.tmOut0, reinterpret_cast<const void*>(out_s + (size_t)ew * kSlabBytes), nc, mr);
         }
         bulk_commit();
       }
       if constexpr (MODE == SCOT_EPI_GELU_BWD) {
-        // bias gradient: column sums of the bf16 values just staged (rows >= M hold zeros: their A rows were zero-filled)
-        const int cp = et & 31, rg = et >> 5;
-        const uint32_t chunk = (uint32_t)(cp >> 2), word = (uint32_t)(cp & 3) * 4;
-        const uint32_t obase = smem_u32(out_s) + word;
+        // bias gradient: column sums of the bf16 values just staged (rows >= M hold zeros: their A rows were zero-filled).
+        // Lane = (column pair p, row parity): even / odd rows sit in different bank halves, so the reads are conflict-free.
+        const uint32_t p = (uint32_t)(lane & 15), par = (uint32_t)(lane >> 4);
 #pragma unroll
-        for (int rr = 0; rr < 16; ++rr) {
-          const int r = rg * 16 + rr;
-          const float2 f = unpack_bf16x2(lds32(obase + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4)));
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t r = 2u * (uint32_t)i + par;
+          const float2 f = unpack_bf16x2(lds32(slab0 + r * 64u + ((((p >> 2)) ^ ((r >> 1) & 3u)) << 4) + (p & 3u) * 4u));
           cs0 += f.x;
           cs1 += f.y;
         }
         const bool last_of_col = (t + 1 >= t_end) || ((t + 1) / ga.tiles_m != cb);
-        if (last_of_col && ga.colsum != nullptr) {
-          const int c = n0 + 2 * cp;
-          if (c < ga.N) atomicAdd(ga.colsum + c, cs0);
-          if (c + 1 < ga.N) atomicAdd(ga.colsum + c + 1, cs1);
+        if (last_of_col) {
+          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16);
+          cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+          if (ga.colsum != nullptr && lane < 16) {
+            const int c = nc + 2 * (int)p;
+            if (c < ga.N) atomicAdd(ga.colsum + c, cs0);
+            if (c + 1 < ga.N) atomicAdd(ga.colsum + c + 1, cs1);
+          }
           cs0 = cs1 = 0.f;
         }
       }
     }
-    if (issuer) bulk_wait<0>();  // all stores of this CTA are performed before the grid can complete
+    if (lane == 0) bulk_wait<0>();  // all stores of this warp are performed before the grid can complete
   }
   tc_fence_before();
   __syncthreads();
@@ -847,13 +856,13 @@ int launch_async(const void* A, long lda, const void* B, long ldb, int M, int N,
   if (rc) return rc;
   if (MODE == SCOT_EPI_GELU) {
     if (ep.out0 != nullptr) {
-      rc = make_tmap(&ga.tmOut0, ep.out0, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld0, 64, BM);
+      rc = make_tmap(&ga.tmOut0, ep.out0, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld0, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
     }
-    rc = make_tmap(&ga.tmOut1, ep.out1, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld1, 64, BM);
+    rc = make_tmap(&ga.tmOut1, ep.out1, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld1, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
   } else {
-    rc = make_tmap(&ga.tmOut0, ep.out0, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld0, 64, BM);
+    rc = make_tmap(&ga.tmOut0, ep.out0, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ld0, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     ga.tmOut1 = ga.tmOut0;
   }
@@ -897,7 +906,8 @@ bool tma_ok(const void* p, long ld) { return p == nullptr || ((((uintptr_t)p) & 
 template <int AMN, int BMN, int MODE>
 int dispatch_bn(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiArgs& ep,
                 cudaStream_t stream) {
-  // bf16-output modes: async-epilogue kernel (TMA stores, TMA-fed auxiliary operand), 128 x 64 tiles, two CTAs per SM
+  // bf16-output modes: async-epilogue kernel (warp-private TMA stores, TMA-fed auxiliary operand), 128 x 64 tiles, two CTAs
+  // per SM. 128 x 128 tiles at one CTA per SM were measured slower for every stage shape (GELU: 31.6 vs 14.9 us at 4096 x 1536 x 384)
   if constexpr (AMN == 0 && (MODE == SCOT_EPI_GELU || MODE == SCOT_EPI_GELU_BWD || MODE == SCOT_EPI_BF16)) {
     if (async_epi_enabled() && ep.lo_off == 0 && tma_ok(ep.out0, ep.ld0) && tma_ok(ep.out1, ep.ld1) && tma_ok(ep.aux, ep.ldaux) &&
         (MODE != SCOT_EPI_GELU || ep.out1 != nullptr) && (MODE != SCOT_EPI_GELU_BWD || ep.aux != nullptr) &&
