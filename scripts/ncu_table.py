@@ -1,5 +1,7 @@
-"""Markdown table + traffic JSON from .ncu-rep files (ncu --set full captures), one row per kernel name (mean over the
-captured launches): duration, DRAM bytes read / written per launch, DRAM %, tensor-pipe %, issue-slot %, registers.
+"""Markdown table + traffic JSON from .ncu-rep files, one row per kernel name: launches captured, mean and largest
+duration, DRAM bytes read / written per launch (mean; the JSON holds read + write of the LARGEST launch of each kernel,
+i.e. its stage-0 instance — the one bench.py times), DRAM %, tensor-pipe %, issue-slot %, registers. A kernel that appears
+in several reports keeps the row of the first report that has it.
 
     python scripts/ncu_table.py out.md traffic.json rep1.ncu-rep [rep2 ...]
 """
@@ -32,6 +34,8 @@ def main():
         for r in rows[2:]:
             name = re.sub(r"\(anonymous namespace\)::|<unnamed>::|^void ", "", r[ik])
             name = re.sub(r"\(.*$", "", name)
+            if name in agg and agg[name]["rep"] != [rep.split("/")[-1]]:
+                continue
             d = agg.setdefault(name, collections.defaultdict(list))
             for k, i in col.items():
                 try:
@@ -40,14 +44,17 @@ def main():
                     pass
             d["rep"] = [rep.split("/")[-1]]
     mean = lambda v: sum(v) / len(v) if v else float("nan")
-    lines = ["| kernel | launches | us | DRAM read MB | DRAM write MB | DRAM % | tensor pipe % | issue % | regs | grid x block | capture |",
-             "|---|---|---|---|---|---|---|---|---|---|---|"]
+    lines = ["| kernel | launches | us (mean) | us (max) | DRAM read MB | DRAM write MB | DRAM % | tensor pipe % | issue % | regs | grid x block | capture |",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|"]
     traffic = {}
     for name, d in agg.items():
-        lines.append(f"| `{name}` | {len(d['t'])} | {mean(d['t']):.1f} | {mean(d['r']) / 1e6:.2f} | {mean(d['w']) / 1e6:.2f} | "
+        lines.append(f"| `{name}` | {len(d['t'])} | {mean(d['t']):.1f} | {max(d['t']):.1f} | {mean(d['r']) / 1e6:.2f} | {mean(d['w']) / 1e6:.2f} | "
                      f"{mean(d['dram']):.1f} | {mean(d['tensor']):.1f} | {mean(d['issue']):.1f} | {mean(d['regs']):.0f} | "
                      f"{mean(d['grid']):.0f} x {mean(d['block']):.0f} | {d['rep'][0]} |")
-        traffic[name.split("<")[0]] = traffic.get(name.split("<")[0]) or (mean(d["r"]) + mean(d["w"]))
+        big = max(a + b for a, b in zip(d["r"], d["w"])) if d["r"] and d["w"] else None
+        key = name.split("<")[0]
+        traffic[key] = max(traffic.get(key) or 0, big or 0) or None
+        traffic[name] = big
     open(out_md, "w").write("\n".join(lines) + "\n")
     json.dump(traffic, open(out_json, "w"), indent=1)
     print("\n".join(lines))
