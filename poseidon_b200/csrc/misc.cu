@@ -150,26 +150,38 @@ scale_add_bwd_kernel(const float* __restrict__ g, const bf16* __restrict__ zb, c
 }
 
 // ---- depthwise 7x7 (NHWC fp32, zero padding 3) -------------------------------------------------------
-// One thread = 8 consecutive x positions x 4 channels: per filter row it loads 14 input float4 and 28 weights for
-// 224 FMAs (register sliding window) instead of one load per FMA.
+// One thread = 8 consecutive x positions x 4 channels: per filter row it loads 14 input float4 for 224 FMAs (register
+// sliding window). The filter is staged once per block in shared memory, tap-major ([49][C], already flipped for the data
+// gradient), so the inner loop reads its four weights with one conflict-free LDS.128 instead of four strided global loads.
 // FLIP=false: out = conv(x, w) + bias ; FLIP=true (data gradient): out = add + conv(x, flipped w)
 template <bool FLIP>
 __global__ void __launch_bounds__(128)
 dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-               const float* __restrict__ add, float* __restrict__ out, int B, int res, int C) {
-  const int c4n = C / 4, xg = (res + 7) / 8;
-  const long total = (long)B * res * xg * c4n;
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c4 = (int)(i % c4n);
-  long t = i / c4n;
+               const float* __restrict__ add, float* __restrict__ out, int B, int res, int C, int cqb) {
+  // block = (chunk of `cqb` channel quads, 128 / cqb groups of 8 x positions); blockIdx.y = channel chunk. Blocks are
+  // persistent (a few per SM) and stride over the pixel groups, so the filter is staged once per block: coalesced reads of
+  // w[c][49], transposed into [49][CB + 4] (pitch + 4 floats: float4-aligned rows, 4-way instead of 32-way store conflicts)
+  extern __shared__ __align__(16) float sw[];
+  const int CB = 4 * cqb, WP = CB + 4, cbase = blockIdx.y * CB;
+  for (int j = threadIdx.x; j < 49 * CB; j += blockDim.x) {
+    const int cc = j / 49, tap = j - cc * 49;
+    sw[(FLIP ? 48 - tap : tap) * WP + cc] = w[(long)cbase * 49 + j];
+  }
+  __syncthreads();
+  const int xg = (res + 7) / 8, G = blockDim.x / cqb;
+  const int cq = threadIdx.x % cqb, gl = threadIdx.x / cqb;
+  const long items = (long)B * res * xg;
+  if (gl >= G) return;
+  const int cl = cq * 4, c = cbase + cl;
+  const float4 bz = bias != nullptr ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long it = (long)blockIdx.x * G + gl; it < items; it += (long)gridDim.x * G) {
+  long t = it;
   const int gx = (int)(t % xg);
   t /= xg;
   const int py = (int)(t % res);
   const int b = (int)(t / res);
-  const int c = c4 * 4, x0 = gx * 8;
+  const int x0 = gx * 8;
   float4 acc[8];
-  const float4 bz = bias != nullptr ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = bz;
 #pragma unroll 1
@@ -183,16 +195,16 @@ dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
       const int xx = x0 + k - 3;
       in[k] = (xx >= 0 && xx < res) ? *reinterpret_cast<const float4*>(rowp + (long)xx * C) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    const float* wrow = sw + (ky * 7) * WP + cl;
 #pragma unroll
     for (int kx = 0; kx < 7; ++kx) {
-      const int tap = FLIP ? (6 - ky) * 7 + (6 - kx) : ky * 7 + kx;
-      const float w0 = w[(c + 0) * 49 + tap], w1 = w[(c + 1) * 49 + tap], w2 = w[(c + 2) * 49 + tap], w3 = w[(c + 3) * 49 + tap];
+      const float4 wv = *reinterpret_cast<const float4*>(wrow + kx * WP);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        acc[k].x = fmaf(in[k + kx].x, w0, acc[k].x);
-        acc[k].y = fmaf(in[k + kx].y, w1, acc[k].y);
-        acc[k].z = fmaf(in[k + kx].z, w2, acc[k].z);
-        acc[k].w = fmaf(in[k + kx].w, w3, acc[k].w);
+        acc[k].x = fmaf(in[k + kx].x, wv.x, acc[k].x);
+        acc[k].y = fmaf(in[k + kx].y, wv.y, acc[k].y);
+        acc[k].z = fmaf(in[k + kx].z, wv.z, acc[k].z);
+        acc[k].w = fmaf(in[k + kx].w, wv.w, acc[k].w);
       }
     }
   }
@@ -208,17 +220,18 @@ dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
     }
     *reinterpret_cast<float4*>(out + o) = v;
   }
+  }
 }
 // weight gradient: g_w[c,ky,kx] += sum_{b,y,x} dout[b,y,x,c] * x[b,y+ky-3,x+kx-3,c]
 // block = (filter row ky, group of images); thread = (channel quad, row lane) sweeps image rows with a 7-wide
 // register window, accumulating its 7x4 taps; block-level smem reduction, then one atomic per tap per block.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dout, float* __restrict__ g_w, int B, int res,
                      int C, int imgs_per_block) {
   extern __shared__ float sred[];  // [28][C/4] accumulated with smem atomics
   const int c4n = C / 4;
   const int ky = blockIdx.x;
-  const int b0 = blockIdx.y * imgs_per_block;
+  (void)imgs_per_block;
   const int lanes = blockDim.x / c4n;            // row lanes
   const int c4 = threadIdx.x % c4n, rl = threadIdx.x / c4n;
   for (int k = threadIdx.x; k < 28 * c4n; k += blockDim.x) sred[k] = 0.f;
@@ -228,31 +241,34 @@ dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dout
     float4 acc[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int nrows = imgs_per_block * res;
-    for (int r = rl; r < nrows; r += lanes) {
-      const int b = b0 + r / res, y = r % res;
-      if (b >= B) break;
+    // the B * res image rows are dealt round-robin to (block, row lane): every block gets the same share whatever B is
+    const int nrows = B * res;
+    for (int r = blockIdx.y * lanes + rl; r < nrows; r += gridDim.y * lanes) {
+      const int b = r / res, y = r % res;
       const int yy = y + ky - 3;
       if (yy < 0 || yy >= res) continue;
       const float* inrow = x + (((long)b * res + yy) * res) * C + c;
       const float* drow = dout + (((long)b * res + y) * res) * C + c;
-      float4 win[7];  // win[kx] = in[x + kx - 3]
+      // 8 output positions per pass: 14 input + 8 gradient float4 are loaded up front (all independent, so their
+      // latencies overlap), then 8 x 7 x 4 FMAs run from registers
+      for (int x0 = 0; x0 < res; x0 += 8) {
+        float4 in[14], d[8];
 #pragma unroll
-      for (int k = 0; k < 7; ++k) {
-        const int xx = k - 3;
-        win[k] = (xx >= 0 && xx < res) ? *reinterpret_cast<const float4*>(inrow + (long)xx * C) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      for (int xq = 0; xq < res; ++xq) {
-        const float4 d = *reinterpret_cast<const float4*>(drow + (long)xq * C);
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-          acc[k].x = fmaf(d.x, win[k].x, acc[k].x); acc[k].y = fmaf(d.y, win[k].y, acc[k].y);
-          acc[k].z = fmaf(d.z, win[k].z, acc[k].z); acc[k].w = fmaf(d.w, win[k].w, acc[k].w);
+        for (int k = 0; k < 14; ++k) {
+          const int xx = x0 + k - 3;
+          in[k] = (xx >= 0 && xx < res) ? *reinterpret_cast<const float4*>(inrow + (long)xx * C) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
-        const int xn = xq + 4;
-        win[6] = (xn < res) ? *reinterpret_cast<const float4*>(inrow + (long)xn * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 8; ++k)
+          d[k] = (x0 + k < res) ? *reinterpret_cast<const float4*>(drow + (long)(x0 + k) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            acc[kx].x = fmaf(d[k].x, in[k + kx].x, acc[kx].x); acc[kx].y = fmaf(d[k].y, in[k + kx].y, acc[kx].y);
+            acc[kx].z = fmaf(d[k].z, in[k + kx].z, acc[kx].z); acc[kx].w = fmaf(d[k].w, in[k + kx].w, acc[kx].w);
+          }
+        }
       }
     }
 #pragma unroll
@@ -583,25 +599,45 @@ int scot_scale_add_bwd_launch(const float* g, const void* zb, const float* gamma
   SCOT_LAUNCH_CHECK();
   return 0;
 }
-int scot_dwconv7_fwd_launch(const float* x, const float* w, const float* bias, float* out, int B, int res, int C,
-                            cudaStream_t st) {
-  const long total = (long)B * res * ((res + 7) / 8) * (C / 4);
-  dwconv7_kernel<false><<<blocks_for(total, 128), 128, 0, st>>>(x, w, bias, nullptr, out, B, res, C);
+// channel quads per block of the depthwise kernels: the largest divisor of C/4 that is <= 32 (25 KB of staged filter at most)
+static int dw_cqb(int C) {
+  const int c4n = C / 4;
+  int cqb = 1;
+  for (int d = 1; d <= 32 && d <= c4n; ++d)
+    if (c4n % d == 0) cqb = d;
+  return cqb;
+}
+template <bool FLIP>
+static int dwconv7_launch(const float* x, const float* w, const float* bias, const float* add, float* out, int B, int res, int C,
+                          cudaStream_t st) {
+  SCOT_REQUIRE(C % 4 == 0 && C > 0, "dwconv7: channels must be a multiple of 4");
+  const int cqb = dw_cqb(C), G = 128 / cqb;
+  const long items = (long)B * res * ((res + 7) / 8);
+  const int chunks = (C / 4) / cqb;
+  long gx = (items + G - 1) / G;
+  const long cap = (4L * 148 + chunks - 1) / chunks;  // one resident wave: 4 blocks per SM (128 registers x 128 threads), all chunks
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)chunks);
+  dwconv7_kernel<FLIP><<<grid, 128, (size_t)49 * (4 * cqb + 4) * sizeof(float), st>>>(x, w, bias, add, out, B, res, C, cqb);
   SCOT_LAUNCH_CHECK();
   return 0;
 }
+int scot_dwconv7_fwd_launch(const float* x, const float* w, const float* bias, float* out, int B, int res, int C,
+                            cudaStream_t st) {
+  return dwconv7_launch<false>(x, w, bias, nullptr, out, B, res, C, st);
+}
 int scot_dwconv7_bwd_launch(const float* x, const float* w, const float* dout, const float* g_in, float* g_out, float* g_w,
                             int B, int res, int C, cudaStream_t st) {
-  const long total = (long)B * res * ((res + 7) / 8) * (C / 4);
-  dwconv7_kernel<true><<<blocks_for(total, 128), 128, 0, st>>>(dout, w, nullptr, g_in, g_out, B, res, C);
-  SCOT_LAUNCH_CHECK();
+  if (int rc = dwconv7_launch<true>(dout, w, nullptr, g_in, g_out, B, res, C, st)) return rc;
   const int c4n = C / 4;
   SCOT_REQUIRE(c4n <= 256, "dwconv7: at most 1024 channels");
-  // images per block so that ~2 blocks per SM exist for each of the 7 filter rows
-  int ipb = (B * 7 + 295) / 296;
-  if (ipb < 1) ipb = 1;
+  // two resident blocks per SM in total over the 7 filter rows: 42 row groups per filter row
+  int groups = (2 * 148) / 7;
+  const int lanes = 256 / c4n > 0 ? 256 / c4n : 1;
+  const int max_groups = (B * res + lanes - 1) / lanes;
+  if (groups > max_groups) groups = max_groups;
   const size_t smem = (size_t)28 * c4n * sizeof(float);
-  dwconv7_wgrad_kernel<<<dim3(7, (B + ipb - 1) / ipb), 256, smem, st>>>(x, dout, g_w, B, res, C, ipb);
+  dwconv7_wgrad_kernel<<<dim3(7, groups), 256, smem, st>>>(x, dout, g_w, B, res, C, 0);
   SCOT_LAUNCH_CHECK();
   return 0;
 }

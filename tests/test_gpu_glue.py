@@ -112,8 +112,11 @@ def test_recovery_unshuffle_exact_and_conv5(L):
     assert rel(g_w, wr.grad) < 1e-4 and rel(g_b, dD.float().view(-1, OC, ps * ps).sum((0, 2))) < 1e-4
 
 
-def test_convnext_dwconv7_and_layer_scale(L):
-    B, res, C = 2, 16, 32
+@pytest.mark.parametrize("B,res,C", [(2, 16, 32), (1, 12, 96), (1, 8, 192), (1, 4, 384)])
+def test_convnext_dwconv7_and_layer_scale(L, B, res, C):
+    """(1, 12, 96): image width not a multiple of the 8-pixel strip; (1, 8, 192): 24-quad channel chunks leave idle threads;
+    (1, 4, 384): three channel chunks per pixel group, image smaller than the filter"""
+    torch.manual_seed(C)
     x = torch.randn(B, res, res, C, device=dev)
     w = torch.randn(C, 1, 7, 7, device=dev) * 0.1
     b = torch.randn(C, device=dev)
