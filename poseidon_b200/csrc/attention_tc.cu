@@ -107,6 +107,31 @@ __device__ __forceinline__ int quad_code(const TcGeom& g, int bw, int quad) {
   return hm | (wm << 1);
 }
 
+// The two integer divisions of the helpers above, taken once per (window, head) unit: image index, window row / column and
+// the shifted-window edge flags (bit 0: last window row, bit 1: last window column; 0 without shift). The per-step / per-row
+// code then derives region codes and token indices with a few logic ops.
+struct WinPos {
+  int b, wi, wj, edge;
+};
+__device__ __forceinline__ WinPos win_pos(const TcGeom& g, int bw) {
+  const int nw = g.nws * g.nws;
+  WinPos w;
+  w.b = bw / nw;
+  const int r = bw - w.b * nw;
+  w.wi = r / g.nws;
+  w.wj = r - w.wi * g.nws;
+  w.edge = g.shift == 0 ? 0 : ((w.wi == g.nws - 1) ? 1 : 0) | ((w.wj == g.nws - 1) ? 2 : 0);
+  return w;
+}
+__device__ __forceinline__ int quad_code(const WinPos& w, int quad) { return w.edge & (((quad >> 1) & 1) | ((quad & 1) << 1)); }
+__device__ __forceinline__ long token_of(const TcGeom& g, const WinPos& w, int p, int q) {
+  int i = w.wi * 16 + p + g.shift;
+  int j = w.wj * 16 + q + g.shift;
+  if (i >= g.res) i -= g.res;
+  if (j >= g.res) j -= g.res;
+  return ((long)w.b * g.res + i) * g.res + j;
+}
+
 // L2-normalise one token row in place (F.normalize eps 1e-12, HF:445). The row occupies ROWB contiguous bytes; the swizzle
 // only permutes its 16-byte chunks, which a sum of squares / a uniform scale do not care about. Returns 1 / max(|x|, eps).
 template <int HD>
@@ -280,10 +305,11 @@ attn_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
     row_pq(m, pm, qm);
     const float a2 = a.alpha[h] * kLog2e;
     const float* tb = stab + (pm * kTabPitch + qm + 15 * kTabPitch + 15);
-    const int code_m = quad_code(g, bw, m >> 6);
+    const WinPos wp = win_pos(g, bw);
+    const int code_m = quad_code(wp, m >> 6);
     // this thread's columns: quadrants 2 ch and 2 ch + 1
-    const float mt0 = (quad_code(g, bw, 2 * ch) != code_m) ? -200.0f * kLog2e : 0.f;
-    const float mt1 = (quad_code(g, bw, 2 * ch + 1) != code_m) ? -200.0f * kLog2e : 0.f;
+    const float mt0 = (quad_code(wp, 2 * ch) != code_m) ? -200.0f * kLog2e : 0.f;
+    const float mt1 = (quad_code(wp, 2 * ch + 1) != code_m) ? -200.0f * kLog2e : 0.f;
     const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * 128);
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1u;
@@ -346,7 +372,7 @@ attn_tc_fwd_kernel(const __grid_constant__ TcFwdArgs a) {
       }
       umma_commit(bar_mma);
     }
-    const long tr = token_of(g, bw, pm, qm);
+    const long tr = token_of(g, wp, pm, qm);
     l += lds_f32(xch + 1024u + (uint32_t)((ch ^ 1) * 128 + row) * 4u);
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1u;
@@ -586,6 +612,7 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
   for (int u = blockIdx.x; u < a.units; u += gridDim.x) {
     const int h = u / a.nwin, bw = u - h * a.nwin;
     const int unit = bw * g.heads + h;
+    const WinPos wp = win_pos(g, bw);
     if (h != cur_head) {
       if (cur_head >= 0) flush_head(cur_head);
       for (int i = tid; i < kTabN; i += 512) stab[(i / 31) * kTabPitch + (i % 31)] = a.tab2[i * g.heads + h];
@@ -652,7 +679,7 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
       const int quad_n = 2 * kb + (cg >> 1);
       const float* tk = stab + (pm * kTabPitch + qm + 15 * kTabPitch + 15) -
                         ((8 * kb + 4 * (cg & 1)) * kTabPitch + 8 * (cg >> 1));
-      const float c0 = ((quad_code(g, bw, quad_n) != quad_code(g, bw, m >> 6)) ? -200.0f * kLog2e : 0.f) - s_lse[m];
+      const float c0 = ((quad_code(wp, quad_n) != quad_code(wp, m >> 6)) ? -200.0f * kLog2e : 0.f) - s_lse[m];
       const float delta = s_delta[m];
       const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(cg * 32);
       mbar_wait(bar_s, ph_s);
@@ -761,7 +788,7 @@ attn_tc_bwd_kernel(const __grid_constant__ TcBwdArgs a) {
       tmem_ld_wait();
       int p, q;
       row_pq(r, p, q);
-      const long tr = token_of(g, bw, p, q);
+      const long tr = token_of(g, wp, p, q);
       bf16* dst = a.dqkv + tr * (3L * g.C) + (blk >> 1) * g.C + h * HD;
       if (blk < 4) {
         // through the normalisation: d x = (alpha acc - x_hat (x_hat . alpha acc)) / max(|x|, eps)
