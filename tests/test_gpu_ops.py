@@ -115,10 +115,11 @@ def ref_cln(z, t, aw, ab, cw, cb, eps, T):
 
 
 @pytest.mark.parametrize("C", [16, 48, 96, 192, 384, 768])
-@pytest.mark.parametrize("cond", [True, False])
-def test_cln_forward_backward(L, C, cond):
+@pytest.mark.parametrize("cond,Bn,T", [(True, 3, 64), (False, 3, 64), (True, 5, 20), (True, 2, 256)])
+def test_cln_forward_backward(L, C, cond, Bn, T):
+    """T = 64 / 256: one-sample-per-block kernels (rows per block divides T); T = 20 with a conditioned norm: no block size
+    divides the sample, the generic kernels (per-row lead time, blocks spanning samples) run"""
     torch.manual_seed(C)
-    Bn, T = 3, 64
     rows = Bn * T
     z = torch.randn(rows, C, device=dev, dtype=torch.float64) * 2 + 0.5
     res = torch.randn(rows, C, device=dev, dtype=torch.float64)
