@@ -6,7 +6,9 @@
 // Call sites fused here: ScOTLayer res-post-norm adds (model.py:570,574), ScOTEmbeddings.norm (:352),
 // ScOTPatchMerging.norm (:710), ScOTPatchUnmerging permute+norm (:748-759), ConvNeXtBlock.norm (:208).
 // HBM-bound: one (sub-)warp per token row, 128-bit loads, shuffle reductions, row kept in registers.
-#include <cstdlib>
+// Two kernel families: cln_*_rows_kernel (a block's rows belong to one sample: lead time and scale / shift vectors are block
+// constants, two rows in flight per (sub-)warp — the path of every shipped configuration up to C = 768) and cln_*_kernel
+// (per-row lead time; blocks may span samples; C = 1536).
 
 #include "common.cuh"
 #include "internal.h"
@@ -677,14 +679,9 @@ template <int LPR, int V>
 int launch_fwd(const ClnFwdArgs& a, cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
   const int warps = 8;
-  static int force_span = -1;  // A/B knob: SCOT_CLN_SPAN=1 keeps the generic kernels everywhere
-  if (force_span < 0) {
-    const char* e = getenv("SCOT_CLN_SPAN");
-    force_span = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
   if constexpr (V <= 6) {
     constexpr int R = (V <= 3) ? 2 : 1;
-    const int rpb = force_span ? 0 : rows_kernel_rpb(a.rows, a.rows_per_sample, a.time != nullptr, 8L * RPW * R, 8L * RPW,
+    const int rpb = rows_kernel_rpb(a.rows, a.rows_per_sample, a.time != nullptr, 8L * RPW * R, 8L * RPW,
                                                      (long)num_sms() * (V <= 3 ? 2 : 1));
     if (rpb > 0) {
       const long blocks = (a.rows + rpb - 1) / rpb;
@@ -706,13 +703,8 @@ template <int LPR, int V, bool SPLIT>
 int launch_bwd_t(const ClnBwdArgs& a_in, cudaStream_t st) {
   ClnBwdArgs a = a_in;
   constexpr bool kRowsKernel = (4 * LPR * V <= 768) || V <= 6;  // [8][3][C] floats of smem: C <= 768 (wider rows: generic path)
-  static int force_span = -1;  // A/B knob: SCOT_CLN_SPAN=1 keeps the generic kernel everywhere
-  if (force_span < 0) {
-    const char* e = getenv("SCOT_CLN_SPAN");
-    force_span = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
   if constexpr (kRowsKernel) {
-    if (!force_span && a.rows_per_block <= 0 && a.C <= 768) {
+    if (a.rows_per_block <= 0 && a.C <= 768) {
       constexpr int R = (V <= 3 && !SPLIT) ? 2 : 1;
       const int rpb = rows_kernel_rpb(a.rows, a.rows_per_sample, a.time != nullptr, 8L * (32 / LPR) * R, 8L * (32 / LPR),
                                       (long)num_sms() * ((V <= 3 && !SPLIT) ? 2 : 1));
@@ -769,15 +761,7 @@ int scot_cln_bwd_launch(const float* dy, const void* zhat, const float* rstd, co
   SCOT_REQUIRE(C % 4 == 0 && rows > 0, "cln_bwd: bad shape");
   SCOT_REQUIRE((aw == nullptr) == (g_aw == nullptr) && (g_aw == nullptr) == (g_cw == nullptr), "cln_bwd: aw/g_aw/g_cw mismatch");
   SCOT_REQUIRE(aw == nullptr || time != nullptr, "cln_bwd: conditioned norm needs time");
-  long rpb = 0;  // 0: sized by launch_bwd (one resident wave); SCOT_CLN_RPB=<rows per block> overrides (tuning knob)
-  {
-    static long override_rpb = -1;
-    if (override_rpb < 0) {
-      const char* e = getenv("SCOT_CLN_RPB");
-      override_rpb = e ? atol(e) : 0;
-    }
-    if (override_rpb > 0) rpb = override_rpb;
-  }
+  const long rpb = 0;  // rows per block: sized by the launchers (one resident wave)
   ClnBwdArgs a{dy, (const bf16*)zhat, rstd, time, aw, ab, dz, dz_is_f32, g_aw, g_ab, g_cw, g_cb, g_bias_prev, rows, C,
                rows_per_sample, (int)rpb, perm_res, scot_split_off()};
   CLN_DISPATCH(launch_bwd, a);
